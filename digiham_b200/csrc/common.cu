@@ -1,0 +1,48 @@
+// common.cu — error plumbing and device queries shared by all banks of libdigiham_b200.
+#include "common.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+
+namespace dh {
+
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+int sm_count(int device) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
+        cudaGetLastError();
+        return 148;
+    }
+    return n;
+}
+
+}  // namespace dh
+
+extern "C" {
+
+const char* dh_last_error(void) { return dh::g_error; }
+
+const char* dh_version(void) { return "0.1.0-b200"; }
+
+int dh_device_count(int* count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        if (count) *count = 0;
+        dh::set_error("no CUDA device available: %s", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return DH_E_NODEVICE;
+    }
+    if (count) *count = n;
+    return DH_OK;
+}
+
+}

@@ -1,0 +1,316 @@
+// rrc.cu — K1: root-raised-cosine FIR bank (dh_rrc_*), sm_100a.
+//
+// Replaces Digiham::RrcFilter::RrcFilter::process/filter (reference src/rrc_filter/rrc_filter.cpp:16-34) for N
+// channels at once.  Bit-exact contract: per output sample
+//     sum = 0.0f; for i in 0..nZeros: sum = fl32(sum + fl32(c[i] * x[t - nZeros + i]));  out = fl32(fl64(sum) / gain)
+// i.e. separately rounded products and a strictly ordered float32 accumulation (the x86-64 reference build has
+// no FMA), then one double division rounded to float.  For the two built-in gains the division is replaced by a
+// multiplication with the correctly rounded reciprocal: tests/test_rrc_host.py proves, by exhaustion over all
+// 2^32 float inputs, that fl32(fl64(s) * fl64(1/g)) == fl32(fl64(s) / g) for g in {8.337797030, 16.67711971}.
+//
+// Kernel shape (1-D convolution, FP32-issue bound at 2*(nZeros+1) flop per sample — no tensor cores):
+//   * one CTA = one (channel, time tile) of TILE = 128 threads x R outputs; R = 17 is odd so that the per-thread
+//     windows (stride R floats) fall into 32 different shared-memory banks without any padding;
+//   * the tile and its nZeros-sample halo are brought in by TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) that
+//     signal an mbarrier; outputs leave through shared memory and one bulk store, so every HBM access is a
+//     full-line burst and the SM issue slots are left to FMUL/FADD;
+//   * each thread keeps R accumulators and an R-deep sliding window in registers: per tap it issues R FMUL +
+//     R FADD + one LDS (the window advances by one sample) + one constant-bank tap fetch;
+//   * latency is hidden by occupancy (≈9 KB smem, <64 regs per thread -> many CTAs per SM), not by an
+//     intra-CTA pipeline.
+#include "common.cuh"
+#include "tables.inc"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kThreads = 128;
+constexpr int kR = 17;
+constexpr int kTile = kThreads * kR;  // 2176 outputs per CTA
+constexpr int kMaxZeros = 1024;
+constexpr int kMaxTapsParam = 164;    // taps that travel in the kernel parameter (constant bank 0)
+
+struct TapBlock {
+    float c[kMaxTapsParam];
+};
+
+struct RrcParams {
+    const float* in;
+    float* out;
+    const float* hist_in;   // [channels][nz]  last nz inputs before this call
+    float* hist_out;        // [channels][nz]  last nz inputs after this call
+    const float* taps_g;    // taps in global memory (only used when nz + 1 > kMaxTapsParam)
+    unsigned long long in_pitch;
+    unsigned long long out_pitch;
+    double gain;            // divisor, or its reciprocal when mul_recip != 0
+    int n;
+    int nz;
+    int tiles;
+    int pad_;
+};
+
+// NZ_CT > 0: compile-time tap count; RECIP: scale by the reciprocal gain (built-in filters) instead of dividing
+template <int NZ_CT, bool RECIP>
+__global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant__ RrcParams p,
+                                                          const __grid_constant__ TapBlock taps) {
+    extern __shared__ __align__(128) float s[];   // [nz + kTile] inputs, later reused for kTile outputs
+    __shared__ __align__(8) uint64_t bar;
+
+    const int nz = NZ_CT > 0 ? NZ_CT : p.nz;
+    const int tile = blockIdx.x % p.tiles;
+    const int ch = blockIdx.x / p.tiles;
+    const int t0 = tile * kTile;
+    const int valid = min(kTile, p.n - t0);
+    const float* in_row = p.in + (size_t) ch * p.in_pitch;
+    float* out_row = p.out + (size_t) ch * p.out_pitch;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) {
+        dh::mbar_init(&bar, 1);
+        dh::fence_mbar_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t main_bytes = (uint32_t) ((valid + 3) & ~3) * 4u;
+        const uint32_t halo_bytes = (uint32_t) nz * 4u;
+        dh::mbar_expect_tx(&bar, main_bytes + halo_bytes);
+        const float* halo = tile == 0 ? p.hist_in + (size_t) ch * nz : in_row + t0 - nz;
+        dh::bulk_g2s(s, halo, halo_bytes, &bar);
+        dh::bulk_g2s(s + nz, in_row + t0, main_bytes, &bar);
+    }
+
+    // carry the FIR history across calls: the CTA of the last tile publishes the last nz inputs of the stream
+    if (tile == p.tiles - 1) {
+        const float* hin = p.hist_in + (size_t) ch * nz;
+        float* hout = p.hist_out + (size_t) ch * nz;
+        for (int j = tid; j < nz; j += kThreads) {
+            int idx = p.n - nz + j;
+            hout[j] = idx >= 0 ? in_row[idx] : hin[nz + idx];
+        }
+    }
+
+    // taps that do not fit the parameter block are staged behind the sample tile
+    const bool taps_in_smem = NZ_CT == 0 && nz + 1 > kMaxTapsParam;
+    float* s_taps = s + nz + kTile;
+    if (taps_in_smem) {
+        for (int j = tid; j <= nz; j += kThreads) s_taps[j] = p.taps_g[j];
+        __syncthreads();
+    }
+
+    dh::mbar_wait(&bar, 0);
+
+    // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz
+    const int base = tid * kR;
+    const float* sw = s + base;
+    float acc[kR], w[kR];
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        acc[r] = 0.0f;
+        w[r] = sw[r];
+    }
+
+    const int ntaps = nz + 1;
+    const int full = ntaps / kR;
+    int i0 = 0;
+#pragma unroll 1
+    for (int it = 0; it < full; it++, i0 += kR) {
+        const float* nxt = sw + i0 + kR;
+#pragma unroll
+        for (int k = 0; k < kR; k++) {
+            const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
+#pragma unroll
+            for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
+            // slot k held s[base + i0 + k] (the oldest sample, last used by r = 0); it now receives the
+            // sample that output r = kR-1 needs at the next tap.  Never read past tap index nz.
+            if (i0 + k < nz) w[k] = nxt[k];
+        }
+    }
+    {
+        const int rem = ntaps - i0;   // < kR, identical for all threads
+        const float* nxt = sw + i0 + kR;
+#pragma unroll
+        for (int k = 0; k < kR - 1; k++) {
+            if (k < rem) {
+                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
+#pragma unroll
+                for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
+                if (i0 + k < nz) w[k] = nxt[k];
+            }
+        }
+    }
+
+    // everybody is done reading the input tile: reuse it for the outputs
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < kR; r++) {
+        const double q = RECIP ? __dmul_rn((double) acc[r], p.gain) : __ddiv_rn((double) acc[r], p.gain);
+        s[base + r] = __double2float_rn(q);
+    }
+    dh::fence_async_smem();
+    __syncthreads();
+
+    const int bulk_elems = valid & ~3;
+    if (tid == 0 && bulk_elems > 0) {
+        dh::bulk_s2g(out_row + t0, s, (uint32_t) bulk_elems * 4u);
+        dh::bulk_commit();
+        dh::bulk_wait_read0();
+    }
+    // at most three trailing samples of the stream do not fill a 16-byte unit
+    if (tid < valid - bulk_elems) out_row[t0 + bulk_elems + tid] = s[bulk_elems + tid];
+}
+
+}  // namespace
+
+struct dh_rrc {
+    int device = 0;
+    uint32_t channels = 0;
+    int nz = 0;
+    double gain = 1.0;
+    int mul_recip = 0;
+    TapBlock taps{};
+    float* d_taps = nullptr;   // global copy, used for long custom filters
+    float* d_hist = nullptr;   // [2][channels][nz]
+    int cur = 0;
+};
+
+namespace {
+
+int rrc_build(dh_rrc** out, int device, uint32_t channels, uint32_t nz, double gain, int mul_recip,
+              const float* coeffs) {
+    DH_REQUIRE(out != nullptr, DH_E_INVALID, "dh_rrc_create: out is NULL");
+    *out = nullptr;
+    DH_REQUIRE(channels > 0, DH_E_INVALID, "dh_rrc_create: channels must be > 0");
+    DH_REQUIRE(nz >= 4 && nz % 4 == 0 && nz <= kMaxZeros, DH_E_UNSUPPORTED,
+               "dh_rrc_create: nZeros=%u not supported (multiple of 4, 4..%d)", nz, kMaxZeros);
+    DH_REQUIRE(coeffs != nullptr, DH_E_INVALID, "dh_rrc_create: coeffs is NULL");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        dh::set_error("dh_rrc_create: no CUDA device available (this library has no CPU fallback)");
+        return DH_E_NODEVICE;
+    }
+    DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_rrc_create: device %d out of range", device);
+    dh::DeviceGuard guard(device);
+    dh_rrc* h = new (std::nothrow) dh_rrc();
+    DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_rrc_create: out of host memory");
+    h->device = device;
+    h->channels = channels;
+    h->nz = (int) nz;
+    h->gain = mul_recip ? 1.0 / gain : gain;
+    h->mul_recip = mul_recip;
+    for (uint32_t i = 0; i <= nz && i < (uint32_t) kMaxTapsParam; i++) h->taps.c[i] = coeffs[i];
+    size_t hist_bytes = 2 * (size_t) channels * nz * sizeof(float);
+    cudaError_t e = cudaMalloc(&h->d_hist, hist_bytes);
+    if (e == cudaSuccess) e = cudaMemset(h->d_hist, 0, hist_bytes);
+    if (e == cudaSuccess && nz + 1 > (uint32_t) kMaxTapsParam) {
+        e = cudaMalloc(&h->d_taps, (nz + 1) * sizeof(float));
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_taps, coeffs, (nz + 1) * sizeof(float), cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess) {
+        dh::set_error("dh_rrc_create: %s", cudaGetErrorString(e));
+        cudaFree(h->d_hist);
+        cudaFree(h->d_taps);
+        delete h;
+        return (int) e;
+    }
+    *out = h;
+    return DH_OK;
+}
+
+void bits_to_floats(const uint32_t* bits, int n, std::vector<float>& out) {
+    out.resize(n);
+    std::memcpy(out.data(), bits, n * sizeof(float));
+}
+
+}  // namespace
+
+extern "C" {
+
+int dh_rrc_create(dh_rrc** out, int device, uint32_t channels, int kind) {
+    std::vector<float> taps;
+    if (kind == DH_RRC_WIDE) {
+        bits_to_floats(dh_rrc_wide_taps_bits, DH_RRC_WIDE_NZEROS + 1, taps);
+        return rrc_build(out, device, channels, DH_RRC_WIDE_NZEROS, DH_RRC_WIDE_GAIN, 1, taps.data());
+    }
+    if (kind == DH_RRC_NARROW) {
+        bits_to_floats(dh_rrc_narrow_taps_bits, DH_RRC_NARROW_NZEROS + 1, taps);
+        return rrc_build(out, device, channels, DH_RRC_NARROW_NZEROS, DH_RRC_NARROW_GAIN, 1, taps.data());
+    }
+    if (out) *out = nullptr;
+    dh::set_error("dh_rrc_create: unknown kind %d", kind);
+    return DH_E_INVALID;
+}
+
+int dh_rrc_create_custom(dh_rrc** out, int device, uint32_t channels, uint32_t n_zeros, double gain,
+                         const float* h_coeffs) {
+    return rrc_build(out, device, channels, n_zeros, gain, 0, h_coeffs);
+}
+
+int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
+                   void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_process: handle is NULL");
+    if (n == 0) return DH_OK;
+    DH_REQUIRE(d_in != nullptr && d_out != nullptr, DH_E_INVALID, "dh_rrc_process: NULL buffer");
+    DH_REQUIRE(d_in != d_out, DH_E_INVALID, "dh_rrc_process: in-place operation is not supported");
+    DH_REQUIRE(((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0), DH_E_INVALID,
+               "dh_rrc_process: buffers must be 16-byte aligned");
+    const size_t n4 = (n + 3) & ~(size_t) 3;
+    DH_REQUIRE(in_pitch % 4 == 0 && out_pitch % 4 == 0 && in_pitch >= n4 && out_pitch >= n4, DH_E_INVALID,
+               "dh_rrc_process: pitches must be multiples of 4 and >= n rounded up to 4 (n=%zu in=%zu out=%zu)", n,
+               in_pitch, out_pitch);
+    DH_REQUIRE(n <= 0x7fffffffu - kTile, DH_E_INVALID, "dh_rrc_process: n too large");
+    const size_t tiles = (n + kTile - 1) / kTile;
+    DH_REQUIRE(tiles * h->channels <= 0x7fffffffu, DH_E_INVALID, "dh_rrc_process: channels x tiles too large");
+
+    dh::DeviceGuard guard(h->device);
+    RrcParams p;
+    p.in = d_in;
+    p.out = d_out;
+    const size_t hist_elems = (size_t) h->channels * h->nz;
+    p.hist_in = h->d_hist + (size_t) h->cur * hist_elems;
+    p.hist_out = h->d_hist + (size_t) (h->cur ^ 1) * hist_elems;
+    p.taps_g = h->d_taps;
+    p.in_pitch = in_pitch;
+    p.out_pitch = out_pitch;
+    p.gain = h->gain;
+    p.n = (int) n;
+    p.nz = h->nz;
+    p.tiles = (int) tiles;
+    p.pad_ = 0;
+
+    cudaStream_t st = (cudaStream_t) stream;
+    const unsigned grid = (unsigned) (tiles * h->channels);
+    size_t smem = (size_t) (h->nz + kTile) * sizeof(float);
+    if (h->nz == 80 && h->mul_recip) {
+        rrc_fir_kernel<80, true><<<grid, kThreads, smem, st>>>(p, h->taps);
+    } else if (h->nz == 160 && h->mul_recip) {
+        rrc_fir_kernel<160, true><<<grid, kThreads, smem, st>>>(p, h->taps);
+    } else {
+        if (h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
+        rrc_fir_kernel<0, false><<<grid, kThreads, smem, st>>>(p, h->taps);
+    }
+    DH_CUDA(cudaGetLastError());
+    h->cur ^= 1;
+    return DH_OK;
+}
+
+int dh_rrc_reset(dh_rrc* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_reset: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    DH_CUDA(cudaMemsetAsync(h->d_hist, 0, 2 * (size_t) h->channels * h->nz * sizeof(float), (cudaStream_t) stream));
+    h->cur = 0;
+    return DH_OK;
+}
+
+void dh_rrc_destroy(dh_rrc* h) {
+    if (!h) return;
+    dh::DeviceGuard guard(h->device);
+    cudaFree(h->d_hist);
+    cudaFree(h->d_taps);
+    delete h;
+}
+
+}  // extern "C"

@@ -1,0 +1,83 @@
+/*
+ * digiham_b200.h — the C ABI of libdigiham_b200.so: the drop-in boundary of the B200 hot path.
+ *
+ * Every object below is a *bank*: N independent channels of one reference module, living on one GPU.
+ * Channel c of a bank behaves bit-for-bit like one instance of the reference module it replaces, fed
+ * with row c of the sample block.  All state (FIR history, timing-recovery rings, decoder phase) is
+ * carried inside the bank between calls, so results do not depend on how a stream is cut into calls.
+ *
+ * Conventions
+ *   - plain C, opaque handles, no C++/torch types in any signature;
+ *   - d_* pointers are DEVICE pointers on the bank's GPU, h_* pointers are HOST pointers;
+ *   - sample/symbol blocks are channel-major: element (c, t) lives at base[c * pitch + t], pitch in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream); calls are
+ *     asynchronous on that stream unless documented otherwise;
+ *   - return value: DH_OK (0), a negative DH_E_* code, or a positive cudaError_t value;
+ *     dh_last_error() returns the message of the last failure on the calling thread;
+ *   - there is NO CPU fallback: without a CUDA device every create call fails.
+ *
+ * Reference interfaces replaced (paths relative to the reference tree, jketterl/digiham @ 410853c):
+ *   dh_rrc_*      Digiham::RrcFilter::{RrcFilter,WideRrcFilter,NarrowRrcFilter}   include/rrc_filter.hpp:10-31
+ *                 RrcFilter::process(float*, float*, size_t)                      src/rrc_filter/rrc_filter.cpp:16-34
+ */
+#ifndef DIGIHAM_B200_H
+#define DIGIHAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define DH_API __attribute__((visibility("default")))
+#else
+#define DH_API
+#endif
+
+#define DH_OK 0
+#define DH_E_INVALID (-1)     /* bad argument (null handle, misaligned pointer, pitch too small ...) */
+#define DH_E_NOMEM (-2)       /* host allocation failed */
+#define DH_E_STATE (-3)       /* call not valid in the current state of the bank */
+#define DH_E_UNSUPPORTED (-4) /* configuration not supported by the CUDA path */
+#define DH_E_NODEVICE (-5)    /* no usable sm_100 device */
+
+DH_API const char* dh_last_error(void);
+/* version of this library, formatted like Digiham::version (include/version.hpp:7) */
+DH_API const char* dh_version(void);
+/* number of CUDA devices visible to the library; DH_E_NODEVICE if there is none */
+DH_API int dh_device_count(int* count);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * RRC FIR bank — N x Digiham::RrcFilter::RrcFilter (include/rrc_filter.hpp:10-31).
+ *
+ * out[c][t] = (float)((double) sum / gain), sum = ((0.0f + c0*x[t-nZeros]) + c1*x[t-nZeros+1]) + ... in that
+ * order, each product and each partial sum rounded to float32, no FMA (src/rrc_filter/rrc_filter.cpp:22-34).
+ * Samples before the first one ever processed read as 0 (the reference leaves them uninitialised,
+ * src/rrc_filter/rrc_filter.cpp:9).
+ */
+typedef struct dh_rrc dh_rrc;
+
+#define DH_RRC_WIDE 0   /* WideRrcFilter:   81 taps, gain 8.337797030  (src/rrc_filter/rrc_filter.cpp:89-115) */
+#define DH_RRC_NARROW 1 /* NarrowRrcFilter: 161 taps, gain 16.67711971 (src/rrc_filter/rrc_filter.cpp:39-84)  */
+
+DH_API int dh_rrc_create(dh_rrc** out, int device, uint32_t channels, int kind);
+/* RrcFilter(nZeros, gain, coeffs) (include/rrc_filter.hpp:12): h_coeffs holds nZeros+1 taps; nZeros must be a
+ * multiple of 4 and <= 1024. */
+DH_API int dh_rrc_create_custom(dh_rrc** out, int device, uint32_t channels, uint32_t n_zeros, double gain,
+                         const float* h_coeffs);
+/* Filters n samples of every channel.  d_in/d_out must be 16-byte aligned, both pitches multiples of 4 and
+ * >= n rounded up to 4 (up to 3 elements of padding after sample n-1 may be read, none is written).
+ * In-place operation (d_out == d_in) is not supported. */
+DH_API int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
+                   void* stream);
+/* back to power-on state (zero history) */
+DH_API int dh_rrc_reset(dh_rrc* h, void* stream);
+DH_API void dh_rrc_destroy(dh_rrc* h);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DIGIHAM_B200_H */
