@@ -13,8 +13,9 @@ from ._capi import (  # noqa: F401
     lib,
     lib_path,
     RrcBank,
+    DemodBank,
     RRC_WIDE,
     RRC_NARROW,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "RRC_WIDE", "RRC_NARROW"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "RRC_WIDE", "RRC_NARROW"]

@@ -48,6 +48,16 @@ def lib():
     L.dh_rrc_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_rrc_destroy.argtypes = [ctypes.c_void_p]
     L.dh_rrc_destroy.restype = None
+    L.dh_demod_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_uint32,
+                                  ctypes.c_int]
+    L.dh_demod_reserve.argtypes = [ctypes.c_void_p, ctypes.c_size_t, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_demod_max_symbols.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+    L.dh_demod_max_symbols.restype = ctypes.c_size_t
+    L.dh_demod_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                   ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_demod_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_demod_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_demod_destroy.restype = None
     _lib = L
     return L
 
@@ -107,6 +117,63 @@ class RrcBank:
     def close(self):
         if self._h:
             lib().dh_rrc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DemodBank:
+    """N x Digiham::Fsk::GfskDemodulator / FskDemodulator (reference include/gfsk_demodulator.hpp:12-33,
+    include/fsk_demodulator.hpp:12-33) on one GPU."""
+
+    def __init__(self, channels, sps=10, four_level=True, invert=False, device="cuda:0"):
+        self._h = ctypes.c_void_p()
+        self.channels = int(channels)
+        self.sps = int(sps)
+        self.device = torch.device(device)
+        check(lib().dh_demod_create(ctypes.byref(self._h), _dev_index(device), self.channels, int(four_level),
+                                    self.sps, int(invert)))
+
+    def max_symbols(self, n):
+        return lib().dh_demod_max_symbols(self._h, n)
+
+    def reserve(self, max_n):
+        """Returns (device pointer, pitch) of the zero-copy input block."""
+        ptr = ctypes.c_void_p()
+        pitch = ctypes.c_size_t()
+        check(lib().dh_demod_reserve(self._h, max_n, ctypes.byref(ptr), ctypes.byref(pitch)))
+        return ptr.value, pitch.value
+
+    def process(self, x, n=None, sym=None, nsym=None, stream=None):
+        """x: float32 CUDA tensor [channels, >=n] or a (ptr, pitch) pair from reserve()."""
+        if isinstance(x, tuple):
+            ptr, pitch = x
+            assert n is not None
+            dev = self.device
+        else:
+            assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] == self.channels
+            ptr, pitch = x.data_ptr(), x.stride(0)
+            dev = x.device
+            if n is None:
+                n = x.shape[1]
+        if sym is None:
+            sym = torch.empty((self.channels, self.max_symbols(n)), dtype=torch.uint8, device=dev)
+        if nsym is None:
+            nsym = torch.empty((self.channels,), dtype=torch.int32, device=dev)
+        check(lib().dh_demod_process(self._h, ptr, pitch, n, sym.data_ptr(), sym.stride(0), nsym.data_ptr(),
+                                     _stream_ptr(stream)))
+        return sym, nsym
+
+    def reset(self, stream=None):
+        check(lib().dh_demod_reset(self._h, _stream_ptr(stream)))
+
+    def close(self):
+        if self._h:
+            lib().dh_demod_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

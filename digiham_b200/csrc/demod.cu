@@ -1,0 +1,481 @@
+// demod.cu — K2: 2-/4-level FSK slicer with variance-minimum symbol timing (dh_demod_*), sm_100a.
+//
+// Replaces Digiham::Fsk::GfskDemodulator / FskDemodulator (reference src/gfsk_demodulator/gfsk_demodulator.cpp:18-122,
+// src/fsk_demodulator/fsk_demodulator.cpp:19-112) for N channels at once, bit-exactly.
+//
+// What the reference does per symbol, restated (there is NO Gardner loop and no interpolator):
+//   * read sps samples at the read pointer: `sum` over the middle third, `volume_sum` over all, in order, fp32;
+//   * advance by sps + variance_offset (offset decided at the end of the previous 100-symbol block, so it shifts
+//     every window of the current block except the first one);
+//   * every 100 symbols: per sample phase i, fp32 ordered total -> mean (float divide, widened) -> fp64 ordered
+//     sum of squared deviations -> /100; first strict minimum decides a +-1 sample nudge for the next block;
+//   * push volume_sum/sps into a 100-entry ring, min/max over the ring (max starts at FLT_MIN), thresholds in
+//     mixed float/double arithmetic, slice.
+//
+// GPU shape: the only sequential dependency is the +-1 nudge from one 100-symbol block to the next, so a group of
+// G lanes (half a warp at sps <= 16, a full warp otherwise) owns one channel and walks its blocks in order.
+// Inside a block the window positions are known up front: lanes own symbols for the window sums, then the ring
+// min/max becomes (prefix over this block) x (suffix over the previous block) computed with __shfl_up_sync scans,
+// then lanes own sample phases for the variance search.  Samples are staged block-wise into shared memory with
+// aligned float4 loads.  Partially filled blocks are carried: the unconsumed tail of every channel is moved to the
+// front of its work row, right-aligned against the position where the producer writes the next chunk.
+#include "common.cuh"
+
+#include <cfloat>
+#include <new>
+
+namespace {
+
+constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (include/gfsk_demodulator.hpp:5-6)
+constexpr int kThreads = 128;
+constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
+
+struct ChannelState {
+    float vol_prev[kBlockSyms];  // volume ring content written by the previous block (zeros at power-on)
+    int vo;                      // variance_offset pending for the current block
+    int j_done;                  // symbols of the current block already emitted
+    int carry_len;               // samples kept in front of the work row
+    int pad_;
+};
+
+struct DemodParams {
+    float* work;                 // [channels][pitch]; chunk sample 0 sits at column carry_cap
+    unsigned long long pitch;
+    uint8_t* sym;                // [channels][sym_pitch]
+    unsigned long long sym_pitch;
+    uint32_t* nsym;              // [channels] symbols emitted by this call
+    ChannelState* state;
+    int channels;
+    int n;                       // new samples per channel
+    int sps;
+    int lo, hi;                  // evaluation window [lo, hi)
+    int four_level;
+    int invert;
+    int carry_cap;
+    int samples_cap;             // floats reserved per group for staged samples
+    int group_floats;            // floats of shared memory per group
+};
+
+__device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
+__device__ __forceinline__ float max_gt(float cur, float v) { return v > cur ? v : cur; }
+
+template <int G>
+__device__ __forceinline__ unsigned group_mask() {
+    if (G == 32) return 0xffffffffu;
+    return 0xffffu << ((threadIdx.x & 31) & 16);
+}
+
+// out_min[j] = min(src[0..j]), out_max[j] = max(FLT_MIN, src[0..j]) for j < count (count <= 100)
+template <int G>
+__device__ __forceinline__ void prefix_minmax(const float* src, int count, float* out_min, float* out_max, int gl,
+                                              unsigned gmask) {
+    constexpr int chunk = (kBlockSyms + G - 1) / G;
+    const int j0 = gl * chunk;
+    const int j1 = min(count, j0 + chunk);
+    float mn = FLT_MAX, mx = FLT_MIN;
+    for (int j = j0; j < j1; j++) {
+        const float v = src[j];
+        mn = min_lt(mn, v);
+        mx = max_gt(mx, v);
+        out_min[j] = mn;
+        out_max[j] = mx;
+    }
+    float tmn = mn, tmx = mx;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const float a = __shfl_up_sync(gmask, tmn, d, G);
+        const float b = __shfl_up_sync(gmask, tmx, d, G);
+        if (gl >= d) {
+            tmn = min_lt(tmn, a);
+            tmx = max_gt(tmx, b);
+        }
+    }
+    float emn = __shfl_up_sync(gmask, tmn, 1, G);
+    float emx = __shfl_up_sync(gmask, tmx, 1, G);
+    if (gl == 0) {
+        emn = FLT_MAX;
+        emx = FLT_MIN;
+    }
+    for (int j = j0; j < j1; j++) {
+        out_min[j] = min_lt(out_min[j], emn);
+        out_max[j] = max_gt(out_max[j], emx);
+    }
+}
+
+// out_min[j] = min(src[j+1..99]), out_max[j] = max(FLT_MIN, src[j+1..99]); empty range -> FLT_MAX / FLT_MIN
+template <int G>
+__device__ __forceinline__ void suffix_minmax_exclusive(const float* src, float* out_min, float* out_max, int gl,
+                                                        unsigned gmask) {
+    constexpr int chunk = (kBlockSyms + G - 1) / G;
+    // work on reversed index r = 99 - j: lane owns r in [r0, r1)
+    const int r0 = gl * chunk;
+    const int r1 = min(kBlockSyms, r0 + chunk);
+    float mn = FLT_MAX, mx = FLT_MIN;
+    for (int r = r0; r < r1; r++) {
+        // exclusive: store before absorbing src[99 - r]
+        out_min[kBlockSyms - 1 - r] = mn;
+        out_max[kBlockSyms - 1 - r] = mx;
+        const float v = src[kBlockSyms - 1 - r];
+        mn = min_lt(mn, v);
+        mx = max_gt(mx, v);
+    }
+    float tmn = mn, tmx = mx;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const float a = __shfl_up_sync(gmask, tmn, d, G);
+        const float b = __shfl_up_sync(gmask, tmx, d, G);
+        if (gl >= d) {
+            tmn = min_lt(tmn, a);
+            tmx = max_gt(tmx, b);
+        }
+    }
+    float emn = __shfl_up_sync(gmask, tmn, 1, G);
+    float emx = __shfl_up_sync(gmask, tmx, 1, G);
+    if (gl == 0) {
+        emn = FLT_MAX;
+        emx = FLT_MIN;
+    }
+    for (int r = r0; r < r1; r++) {
+        const int j = kBlockSyms - 1 - r;
+        out_min[j] = min_lt(out_min[j], emn);
+        out_max[j] = max_gt(out_max[j], emx);
+    }
+}
+
+template <int G>
+__global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__ DemodParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;
+    const int grp = threadIdx.x / G;
+    const int ch = blockIdx.x * (kThreads / G) + grp;
+    if (ch >= p.channels) return;   // a whole group leaves together; shuffles below only name the own group
+    const unsigned gmask = group_mask<G>();
+
+    const int sps = p.sps;
+    float* S = smem + (size_t) grp * p.group_floats;   // staged samples of the current block
+    float* vol = S + p.samples_cap;                     // per-symbol volume averages of the current block
+    float* avg = vol + kBlockSyms;                      // per-symbol slicer input
+    float* pmin = avg + kBlockSyms;
+    float* pmax = pmin + kBlockSyms;
+    float* prevv = pmax + kBlockSyms;                   // volumes of the previous block
+    float* smin = prevv + kBlockSyms;
+    float* smax = smin + kBlockSyms;
+    double* var = reinterpret_cast<double*>(smax + kBlockSyms);   // [sps]
+
+    ChannelState* st = p.state + ch;
+    int vo = st->vo;
+    int j_done = st->j_done;
+    const int carry_len = st->carry_len;
+    for (int j = gl; j < kBlockSyms; j += G) prevv[j] = st->vol_prev[j];
+    __syncwarp(gmask);
+    suffix_minmax_exclusive<G>(prevv, smin, smax, gl, gmask);
+    __syncwarp(gmask);
+
+    float* row = p.work + (size_t) ch * p.pitch;
+    const int col0 = p.carry_cap - carry_len;   // column of logical stream index 0
+    const int T = carry_len + p.n;              // samples visible to this call
+    uint8_t* sym_row = p.sym + (size_t) ch * p.sym_pitch;
+    const float fsps = (float) sps;
+    const float fwin = (float) (p.hi - p.lo);
+
+    int P = 0;         // logical index of the current block's first window
+    int emitted = 0;
+    for (;;) {
+        // symbol j of this block starts at P + j*sps + (j >= 1 ? vo : 0) and is processed iff more than
+        // sps + 1 samples are available from there (gfsk_demodulator.cpp:21)
+        int m = 0;
+        if (T - P >= sps + 2) {
+            const int room = T - P - vo - sps - 2;
+            m = 1 + (room >= sps ? min(kBlockSyms - 1, room / sps) : 0);
+        }
+        if (m <= j_done) break;
+
+        // stage [P, P + m*sps + 2) with aligned 16-byte loads; sample P + x lands at S[a0 + x]
+        const int a0 = (col0 + P) & 3;
+        {
+            const float4* src = reinterpret_cast<const float4*>(row + col0 + P - a0);
+            float4* dst = reinterpret_cast<float4*>(S);
+            const int nvec = (a0 + m * sps + 2 + 3) >> 2;
+            for (int v = gl; v < nvec; v += G) dst[v] = src[v];
+        }
+        __syncwarp(gmask);
+
+        // window sums (gfsk_demodulator.cpp:28-35, 82-83, 88)
+        for (int j = gl; j < m; j += G) {
+            const float* w = S + a0 + j * sps + (j ? vo : 0);
+            float sum = 0.0f, vsum = 0.0f;
+            for (int i = 0; i < sps; i++) {
+                const float v = w[i];
+                if (i >= p.lo && i < p.hi) sum = __fadd_rn(sum, v);
+                vsum = __fadd_rn(vsum, v);
+            }
+            vol[j] = __fdiv_rn(vsum, fsps);
+            avg[j] = __fdiv_rn(sum, fwin);
+        }
+        __syncwarp(gmask);
+
+        // ring min/max after symbol j = prefix over this block's volumes x suffix over the previous block's
+        prefix_minmax<G>(vol, m, pmin, pmax, gl, gmask);
+        __syncwarp(gmask);
+
+        // calibrateAudio + slicing (gfsk_demodulator.cpp:88-104, 109-122)
+        for (int j = j_done + gl; j < m; j += G) {
+            const float mn = min_lt(pmin[j], smin[j]);
+            const float mx = max_gt(pmax[j], smax[j]);
+            const float center = __fmul_rn(__fadd_rn(mx, mn), 0.5f);
+            const float a = avg[j];
+            uint8_t s;
+            if (p.four_level) {
+                const double c = (double) center;
+                const float umid = __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mx, center), 0.625), c));
+                const float lmid = __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mn, center), 0.625), c));
+                s = a > center ? (a > umid ? 1 : 0) : (a < lmid ? 3 : 2);
+            } else {
+                s = a > center ? (p.invert ? 0 : 1) : (p.invert ? 1 : 0);
+            }
+            sym_row[emitted + (j - j_done)] = s;
+        }
+        emitted += m - j_done;
+        if (m < kBlockSyms) {
+            j_done = m;
+            break;
+        }
+
+        // variance-minimum phase search over the 100 windows of this block (gfsk_demodulator.cpp:41-80)
+        for (int i = gl; i < sps; i += G) {
+            const float* w0 = S + a0 + i;
+            float total = w0[0];
+            total = __fadd_rn(0.0f, total);
+            for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, w0[k * sps + vo]);
+            const double mean = (double) __fdiv_rn(total, 100.0f);
+            double d = __dsub_rn(mean, (double) w0[0]);
+            double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
+            for (int k = 1; k < kBlockSyms; k++) {
+                d = __dsub_rn(mean, (double) w0[k * sps + vo]);
+                dsum = __dadd_rn(dsum, __dmul_rn(d, d));
+            }
+            var[i] = __ddiv_rn(dsum, 100.0);
+        }
+        __syncwarp(gmask);
+        double vmin = var[0];
+        int vpos = 0;
+        for (int i = 1; i < sps; i++) {
+            const double v = var[i];
+            if (v < vmin) {
+                vmin = v;
+                vpos = i;
+            }
+        }
+        int vo_next = 0;
+        if (vmin <= 0 || vmin > 5000000) {
+            // no decision
+        } else if (vpos > 0 && vpos < sps / 2) {
+            vo_next = +1;
+        } else if (vpos >= sps / 2 && vpos < sps - 1) {
+            vo_next = -1;
+        }
+
+        // next block
+        P += kBlockSyms * sps + vo;
+        vo = vo_next;
+        j_done = 0;
+        for (int j = gl; j < kBlockSyms; j += G) prevv[j] = vol[j];
+        __syncwarp(gmask);
+        suffix_minmax_exclusive<G>(prevv, smin, smax, gl, gmask);
+        __syncwarp(gmask);
+    }
+
+    // carry: state + the unconsumed tail [P, T) moved right-aligned in front of column carry_cap
+    for (int j = gl; j < kBlockSyms; j += G) st->vol_prev[j] = prevv[j];
+    const int keep = T - P;
+    {
+        const float* src = row + col0 + P;
+        float* dst = row + p.carry_cap - keep;
+        if (dst != src) {
+            for (int o = 0; o < keep; o += G) {
+                const int idx = o + gl;
+                const float v = idx < keep ? src[idx] : 0.0f;
+                __syncwarp(gmask);
+                if (idx < keep) dst[idx] = v;
+                __syncwarp(gmask);
+            }
+        }
+    }
+    if (gl == 0) {
+        st->vo = vo;
+        st->j_done = j_done;
+        st->carry_len = keep;
+        p.nsym[ch] = (uint32_t) emitted;
+    }
+}
+
+}  // namespace
+
+struct dh_demod {
+    int device = 0;
+    uint32_t channels = 0;
+    int four_level = 0;
+    int sps = 0;
+    int invert = 0;
+    int lo = 0, hi = 0;
+    int carry_cap = 0;
+    ChannelState* d_state = nullptr;
+    float* d_work = nullptr;
+    size_t pitch = 0;      // elements per work row
+    size_t max_n = 0;      // chunk capacity of the work rows
+};
+
+namespace {
+
+int demod_reserve(dh_demod* h, size_t max_n) {
+    if (h->d_work && max_n <= h->max_n) return DH_OK;
+    const size_t n4 = (max_n + 3) & ~(size_t) 3;
+    const size_t pitch = (size_t) h->carry_cap + n4;
+    float* nw = nullptr;
+    DH_CUDA(cudaMalloc(&nw, (size_t) h->channels * pitch * sizeof(float)));
+    if (h->d_work) {
+        // keep the carried tails; the bank may be mid-stream
+        DH_CUDA(cudaDeviceSynchronize());
+        DH_CUDA(cudaMemcpy2D(nw, pitch * sizeof(float), h->d_work, h->pitch * sizeof(float),
+                             (size_t) h->carry_cap * sizeof(float), h->channels, cudaMemcpyDeviceToDevice));
+        DH_CUDA(cudaFree(h->d_work));
+    } else {
+        DH_CUDA(cudaMemset(nw, 0, (size_t) h->channels * pitch * sizeof(float)));
+    }
+    h->d_work = nw;
+    h->pitch = pitch;
+    h->max_n = n4;
+    return DH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_level, uint32_t sps, int invert) {
+    DH_REQUIRE(out != nullptr, DH_E_INVALID, "dh_demod_create: out is NULL");
+    *out = nullptr;
+    DH_REQUIRE(channels > 0, DH_E_INVALID, "dh_demod_create: channels must be > 0");
+    DH_REQUIRE(sps >= 4 && sps <= 128, DH_E_UNSUPPORTED, "dh_demod_create: samplesPerSymbol=%u not supported (4..128)",
+               sps);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        dh::set_error("dh_demod_create: no CUDA device available (this library has no CPU fallback)");
+        return DH_E_NODEVICE;
+    }
+    DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_demod_create: device %d out of range", device);
+    dh::DeviceGuard guard(device);
+    dh_demod* h = new (std::nothrow) dh_demod();
+    DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_demod_create: out of host memory");
+    h->device = device;
+    h->channels = channels;
+    h->four_level = four_level != 0;
+    h->sps = (int) sps;
+    h->invert = invert != 0;
+    // lowestEval / highestEval (gfsk_demodulator.cpp:8-9): roundf of a float quotient
+    h->lo = (int) roundf((float) sps / 3);
+    h->hi = (int) roundf((float) sps * 2 / 3);
+    h->carry_cap = kBlockSyms * (int) sps + kCarrySlack;
+    cudaError_t e = cudaMalloc(&h->d_state, (size_t) channels * sizeof(ChannelState));
+    if (e == cudaSuccess) e = cudaMemset(h->d_state, 0, (size_t) channels * sizeof(ChannelState));
+    if (e != cudaSuccess) {
+        dh::set_error("dh_demod_create: %s", cudaGetErrorString(e));
+        cudaFree(h->d_state);
+        delete h;
+        return (int) e;
+    }
+    *out = h;
+    return DH_OK;
+}
+
+int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reserve: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    int rc = demod_reserve(h, max_n);
+    if (rc != DH_OK) return rc;
+    if (d_buf) *d_buf = h->d_work + h->carry_cap;
+    if (pitch) *pitch = h->pitch;
+    return DH_OK;
+}
+
+size_t dh_demod_max_symbols(const dh_demod* h, size_t n) {
+    if (!h) return 0;
+    return ((size_t) h->carry_cap + n) / (size_t) (h->sps - 1) + 2;
+}
+
+int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, uint8_t* d_sym, size_t sym_pitch,
+                     uint32_t* d_nsym, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_process: handle is NULL");
+    DH_REQUIRE(d_sym != nullptr && d_nsym != nullptr, DH_E_INVALID, "dh_demod_process: NULL output buffer");
+    DH_REQUIRE(n <= 0x40000000u, DH_E_INVALID, "dh_demod_process: n too large");
+    dh::DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    if (n == 0) {
+        DH_CUDA(cudaMemsetAsync(d_nsym, 0, (size_t) h->channels * sizeof(uint32_t), st));
+        return DH_OK;
+    }
+    DH_REQUIRE(d_in != nullptr, DH_E_INVALID, "dh_demod_process: NULL input buffer");
+    DH_REQUIRE(sym_pitch >= dh_demod_max_symbols(h, n), DH_E_INVALID,
+               "dh_demod_process: sym_pitch %zu too small, need dh_demod_max_symbols(n) = %zu", sym_pitch,
+               dh_demod_max_symbols(h, n));
+    const bool zero_copy = h->d_work && d_in == h->d_work + h->carry_cap && in_pitch == h->pitch && n <= h->max_n;
+    if (!zero_copy) {
+        DH_REQUIRE(in_pitch >= n, DH_E_INVALID, "dh_demod_process: in_pitch < n");
+        int rc = demod_reserve(h, n);
+        if (rc != DH_OK) return rc;
+        DH_CUDA(cudaMemcpy2DAsync(h->d_work + h->carry_cap, h->pitch * sizeof(float), d_in, in_pitch * sizeof(float),
+                                  n * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, st));
+    }
+
+    DemodParams p;
+    p.work = h->d_work;
+    p.pitch = h->pitch;
+    p.sym = d_sym;
+    p.sym_pitch = sym_pitch;
+    p.nsym = d_nsym;
+    p.state = h->d_state;
+    p.channels = (int) h->channels;
+    p.n = (int) n;
+    p.sps = h->sps;
+    p.lo = h->lo;
+    p.hi = h->hi;
+    p.four_level = h->four_level;
+    p.invert = h->invert;
+    p.carry_cap = h->carry_cap;
+    p.samples_cap = (kBlockSyms * h->sps + 2 + 3 + 3 + 3) & ~3;
+    // samples | vol avg pmin pmax prevv smin smax | var (doubles, 8-byte aligned because all counts are even)
+    p.group_floats = p.samples_cap + 7 * kBlockSyms + 2 * ((h->sps + 1) & ~1);
+
+    const int G = h->sps <= 16 ? 16 : 32;
+    const int groups = kThreads / G;
+    const unsigned grid = (h->channels + groups - 1) / groups;
+    const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
+    if (G == 16) {
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        demod_kernel<16><<<grid, kThreads, smem, st>>>(p);
+    } else {
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        demod_kernel<32><<<grid, kThreads, smem, st>>>(p);
+    }
+    DH_CUDA(cudaGetLastError());
+    return DH_OK;
+}
+
+int dh_demod_reset(dh_demod* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reset: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    DH_CUDA(cudaMemsetAsync(h->d_state, 0, (size_t) h->channels * sizeof(ChannelState), (cudaStream_t) stream));
+    return DH_OK;
+}
+
+void dh_demod_destroy(dh_demod* h) {
+    if (!h) return;
+    dh::DeviceGuard guard(h->device);
+    cudaFree(h->d_state);
+    cudaFree(h->d_work);
+    delete h;
+}
+
+}  // extern "C"

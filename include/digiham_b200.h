@@ -19,6 +19,9 @@
  * Reference interfaces replaced (paths relative to the reference tree, jketterl/digiham @ 410853c):
  *   dh_rrc_*      Digiham::RrcFilter::{RrcFilter,WideRrcFilter,NarrowRrcFilter}   include/rrc_filter.hpp:10-31
  *                 RrcFilter::process(float*, float*, size_t)                      src/rrc_filter/rrc_filter.cpp:16-34
+ *   dh_demod_*    Digiham::Fsk::GfskDemodulator(sps)                               include/gfsk_demodulator.hpp:12-33
+ *                 Digiham::Fsk::FskDemodulator(sps, invert)                        include/fsk_demodulator.hpp:12-33
+ *                 canProcess()/process()              src/gfsk_demodulator/gfsk_demodulator.cpp:18-122, src/fsk_demodulator/fsk_demodulator.cpp:19-112
  */
 #ifndef DIGIHAM_B200_H
 #define DIGIHAM_B200_H
@@ -75,6 +78,32 @@ DH_API int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* 
 /* back to power-on state (zero history) */
 DH_API int dh_rrc_reset(dh_rrc* h, void* stream);
 DH_API void dh_rrc_destroy(dh_rrc* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * FSK / GFSK demodulator bank — N x Digiham::Fsk::GfskDemodulator (four_level != 0, symbols 0..3) or
+ * N x Digiham::Fsk::FskDemodulator (four_level == 0, symbols 0/1, optional inversion).
+ *
+ * Implements the reference's variance-minimum timing recovery and 100-symbol min/max slicer exactly
+ * (src/gfsk_demodulator/gfsk_demodulator.cpp:24-122): a symbol is produced whenever more than sps + 1 samples
+ * are buffered, unconsumed samples are carried inside the bank.  volume_rb, which the reference leaves
+ * uninitialised (include/gfsk_demodulator.hpp:27), starts as zeros.
+ */
+typedef struct dh_demod dh_demod;
+
+DH_API int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_level, uint32_t sps, int invert);
+/* Zero-copy input: returns the device address (row of channel 0) and pitch where a producer such as
+ * dh_rrc_process should write the next block of up to max_n samples per channel.  Passing exactly this
+ * pointer/pitch to dh_demod_process skips the staging copy.  The address stays valid until a reserve or
+ * process call needs a larger max_n. */
+DH_API int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch);
+/* upper bound of the symbols one dh_demod_process call with n samples can emit per channel */
+DH_API size_t dh_demod_max_symbols(const dh_demod* h, size_t n);
+/* Consumes n new samples of every channel.  Symbols of channel c are written to d_sym[c * sym_pitch ...], their
+ * count for this call to d_nsym[c].  sym_pitch >= dh_demod_max_symbols(h, n). */
+DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, uint8_t* d_sym,
+                            size_t sym_pitch, uint32_t* d_nsym, void* stream);
+DH_API int dh_demod_reset(dh_demod* h, void* stream);
+DH_API void dh_demod_destroy(dh_demod* h);
 
 #ifdef __cplusplus
 }
