@@ -14,8 +14,12 @@ from ._capi import (  # noqa: F401
     lib_path,
     RrcBank,
     DemodBank,
+    DecoderBank,
+    PROTO_DMR,
+    PROTO_YSF,
+    PROTO_POCSAG,
     RRC_WIDE,
     RRC_NARROW,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "RRC_WIDE", "RRC_NARROW"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]

@@ -9,6 +9,7 @@ _LIB_NAME = "libdigiham_b200.so"
 
 RRC_WIDE = 0
 RRC_NARROW = 1
+PROTO_DMR, PROTO_YSF, PROTO_POCSAG = 0, 1, 2
 
 
 class DhError(RuntimeError):
@@ -58,6 +59,18 @@ def lib():
     L.dh_demod_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_demod_destroy.argtypes = [ctypes.c_void_p]
     L.dh_demod_destroy.restype = None
+    L.dh_decoder_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
+    L.dh_decoder_reserve.argtypes = [ctypes.c_void_p, ctypes.c_size_t, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_decoder_set_slot_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint8]
+    L.dh_decoder_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                     ctypes.c_size_t, ctypes.c_void_p]
+    L.dh_decoder_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_decoder_output.argtypes = [ctypes.c_void_p, ctypes.c_uint32, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_decoder_meta.argtypes = [ctypes.c_void_p, ctypes.c_uint32, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_decoder_totals.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.dh_decoder_clear.argtypes = [ctypes.c_void_p]
+    L.dh_decoder_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_decoder_destroy.restype = None
     _lib = L
     return L
 
@@ -174,6 +187,73 @@ class DemodBank:
     def close(self):
         if self._h:
             lib().dh_demod_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DecoderBank:
+    """N x Digiham::{Dmr,Ysf,Pocsag}::Decoder (reference include/decoder.hpp:17-30) on one GPU."""
+
+    def __init__(self, channels, proto=PROTO_DMR, device="cuda:0"):
+        self._h = ctypes.c_void_p()
+        self.channels = int(channels)
+        self.proto = proto
+        self.device = torch.device(device)
+        check(lib().dh_decoder_create(ctypes.byref(self._h), _dev_index(device), self.channels, proto))
+
+    def reserve(self, max_syms):
+        ptr = ctypes.c_void_p()
+        pitch = ctypes.c_size_t()
+        check(lib().dh_decoder_reserve(self._h, max_syms, ctypes.byref(ptr), ctypes.byref(pitch)))
+        return ptr.value, pitch.value
+
+    def set_slot_filter(self, filt, channel=-1):
+        check(lib().dh_decoder_set_slot_filter(self._h, channel, filt))
+
+    def process(self, sym, nsym, max_nsym=None, stream=None):
+        """sym: uint8 CUDA tensor [channels, >=max_nsym] or (ptr, pitch); nsym: int32 CUDA tensor [channels]."""
+        if isinstance(sym, tuple):
+            ptr, pitch = sym
+            assert max_nsym is not None
+        else:
+            assert sym.is_cuda and sym.dtype == torch.uint8 and sym.dim() == 2 and sym.shape[0] == self.channels
+            ptr, pitch = sym.data_ptr(), sym.stride(0)
+            if max_nsym is None:
+                max_nsym = sym.shape[1]
+        assert nsym.is_cuda and nsym.dtype == torch.int32 and nsym.numel() == self.channels
+        check(lib().dh_decoder_process(self._h, ptr, pitch, nsym.data_ptr(), max_nsym, _stream_ptr(stream)))
+
+    def collect(self, stream=None):
+        check(lib().dh_decoder_collect(self._h, _stream_ptr(stream)))
+
+    def output(self, channel):
+        p = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        check(lib().dh_decoder_output(self._h, channel, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value) if n.value else b""
+
+    def meta(self, channel):
+        p = ctypes.c_void_p()
+        n = ctypes.c_size_t()
+        check(lib().dh_decoder_meta(self._h, channel, ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value) if n.value else b""
+
+    def totals(self):
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib().dh_decoder_totals(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def clear(self):
+        check(lib().dh_decoder_clear(self._h))
+
+    def close(self):
+        if self._h:
+            lib().dh_decoder_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

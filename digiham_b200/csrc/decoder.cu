@@ -1,0 +1,304 @@
+// decoder.cu — generic protocol decoder bank (dh_decoder_*): device buffers, zero-copy symbol hand-off, result
+// collection and host-side metadata replay.  The per-protocol kernels live in dmr.cu / ysf.cu / pocsag.cu.
+//
+// Replaces Digiham::Decoder (reference include/decoder.hpp:17-30, src/lib/decoder.cpp:7-47) for N channels.
+#include "decoder_ops.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <new>
+#include <vector>
+
+using dh::DecEvent;
+using dh::DecIo;
+
+namespace {
+constexpr uint32_t kAccumulate = 2;   // process calls whose results fit between two collects
+}
+
+struct dh_decoder {
+    int device = 0;
+    uint32_t channels = 0;
+    int proto = 0;
+    const dh::ProtoOps* ops = nullptr;
+
+    void* d_states = nullptr;
+    uint8_t* d_sym = nullptr;
+    size_t sym_pitch = 0;
+    size_t max_syms = 0;
+    uint8_t* d_out = nullptr;
+    uint32_t out_cap = 0;
+    DecEvent* d_ev = nullptr;
+    uint32_t ev_cap = 0;
+    uint32_t* d_counts = nullptr;      // [3][channels]: out_len, ev_len, flags
+    uint8_t* d_slot_filter = nullptr;
+    std::vector<uint8_t> h_slot_filter;
+    bool filter_dirty = true;
+
+    uint32_t* h_counts = nullptr;      // pinned, [3][channels]
+    uint8_t* h_out = nullptr;          // pinned staging, grown on demand
+    size_t h_out_bytes = 0;
+    DecEvent* h_ev = nullptr;
+    size_t h_ev_bytes = 0;
+
+    std::vector<dh::ChannelResult> results;
+    std::vector<dh::MetaReplay*> replay;
+    uint64_t total_bytes = 0;
+    uint64_t total_meta = 0;
+};
+
+namespace {
+
+int decoder_collect(dh_decoder* h, cudaStream_t st);
+
+int decoder_reserve(dh_decoder* h, size_t max_syms) {
+    if (h->d_sym && max_syms <= h->max_syms) return DH_OK;
+    const size_t m16 = (max_syms + 15) & ~(size_t) 15;
+    const size_t pitch = (size_t) h->ops->carry_cap + m16;
+    if (h->d_sym) {
+        // mid-stream growth: drain pending results, keep the carried symbol tails
+        DH_CUDA(cudaDeviceSynchronize());
+        int rc = decoder_collect(h, nullptr);
+        if (rc != DH_OK) return rc;
+    }
+    uint8_t* ns = nullptr;
+    DH_CUDA(cudaMalloc(&ns, (size_t) h->channels * pitch));
+    DH_CUDA(cudaMemset(ns, 0, (size_t) h->channels * pitch));
+    if (h->d_sym) {
+        DH_CUDA(cudaMemcpy2D(ns, pitch, h->d_sym, h->sym_pitch, (size_t) h->ops->carry_cap, h->channels,
+                             cudaMemcpyDeviceToDevice));
+        DH_CUDA(cudaFree(h->d_sym));
+        DH_CUDA(cudaFree(h->d_out));
+        DH_CUDA(cudaFree(h->d_ev));
+        h->d_out = nullptr;
+        h->d_ev = nullptr;
+    }
+    h->d_sym = ns;
+    h->sym_pitch = pitch;
+    h->max_syms = m16;
+    h->out_cap = (h->ops->out_bytes(m16) * kAccumulate + 15u) & ~15u;
+    h->ev_cap = h->ops->events(m16) * kAccumulate;
+    DH_CUDA(cudaMalloc(&h->d_out, (size_t) h->channels * h->out_cap));
+    DH_CUDA(cudaMalloc(&h->d_ev, (size_t) h->channels * h->ev_cap * sizeof(DecEvent)));
+    return DH_OK;
+}
+
+int grow_pinned(void** p, size_t* have, size_t need) {
+    if (need <= *have) return DH_OK;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *have = 0;
+    need = need + need / 2 + 4096;
+    DH_CUDA(cudaHostAlloc(p, need, cudaHostAllocDefault));
+    *have = need;
+    return DH_OK;
+}
+
+int decoder_collect(dh_decoder* h, cudaStream_t st) {
+    if (!h->d_out) return DH_OK;
+    const uint32_t n = h->channels;
+    DH_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    DH_CUDA(cudaStreamSynchronize(st));
+    const uint32_t* out_len = h->h_counts;
+    const uint32_t* ev_len = h->h_counts + n;
+    const uint32_t* flags = h->h_counts + 2 * (size_t) n;
+    uint32_t max_out = 0, max_ev = 0, any_flags = 0;
+    for (uint32_t c = 0; c < n; c++) {
+        max_out = std::max(max_out, out_len[c]);
+        max_ev = std::max(max_ev, ev_len[c]);
+        any_flags |= flags[c];
+    }
+    if (max_out) {
+        int rc = grow_pinned((void**) &h->h_out, &h->h_out_bytes, (size_t) n * max_out);
+        if (rc != DH_OK) return rc;
+        DH_CUDA(cudaMemcpy2DAsync(h->h_out, max_out, h->d_out, h->out_cap, max_out, n, cudaMemcpyDeviceToHost, st));
+    }
+    if (max_ev) {
+        const size_t w = (size_t) max_ev * sizeof(DecEvent);
+        int rc = grow_pinned((void**) &h->h_ev, &h->h_ev_bytes, (size_t) n * w);
+        if (rc != DH_OK) return rc;
+        DH_CUDA(cudaMemcpy2DAsync(h->h_ev, w, h->d_ev, (size_t) h->ev_cap * sizeof(DecEvent), w, n,
+                                  cudaMemcpyDeviceToHost, st));
+    }
+    DH_CUDA(cudaMemsetAsync(h->d_counts, 0, 3 * (size_t) n * sizeof(uint32_t), st));
+    DH_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t c = 0; c < n; c++) {
+        dh::ChannelResult& r = h->results[c];
+        if (out_len[c]) {
+            r.bytes.append(reinterpret_cast<const char*>(h->h_out + (size_t) c * max_out), out_len[c]);
+            h->total_bytes += out_len[c];
+        }
+        if (ev_len[c] && h->replay[c]) {
+            const size_t before = r.meta.size();
+            h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
+            h->total_meta += r.meta.size() - before;
+        }
+    }
+    DH_REQUIRE(any_flags == 0, DH_E_STATE,
+               "dh_decoder_collect: device result buffers overflowed (flags 0x%x): collect after every %u process calls",
+               any_flags, kAccumulate);
+    return DH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto) {
+    DH_REQUIRE(out != nullptr, DH_E_INVALID, "dh_decoder_create: out is NULL");
+    *out = nullptr;
+    DH_REQUIRE(channels > 0, DH_E_INVALID, "dh_decoder_create: channels must be > 0");
+    const dh::ProtoOps* ops = nullptr;
+    switch (proto) {
+        case DH_PROTO_DMR: ops = dh::dmr_ops(); break;
+        default: break;
+    }
+    DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "dh_decoder_create: protocol %d not supported", proto);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        dh::set_error("dh_decoder_create: no CUDA device available (this library has no CPU fallback)");
+        return DH_E_NODEVICE;
+    }
+    DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_decoder_create: device %d out of range", device);
+    dh::DeviceGuard guard(device);
+    dh_decoder* h = new (std::nothrow) dh_decoder();
+    DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_decoder_create: out of host memory");
+    h->device = device;
+    h->channels = channels;
+    h->proto = proto;
+    h->ops = ops;
+    h->h_slot_filter.assign(channels, 3);
+    h->results.resize(channels);
+    h->replay.assign(channels, nullptr);
+    if (ops->make_replay) {
+        for (uint32_t c = 0; c < channels; c++) h->replay[c] = ops->make_replay();
+    }
+    std::vector<uint8_t> init((size_t) channels * ops->state_size);
+    ops->init_states(init.data(), channels);
+    cudaError_t e = cudaMalloc(&h->d_states, init.size());
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_states, init.data(), init.size(), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, 3 * (size_t) channels * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, 3 * (size_t) channels * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_slot_filter, channels);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**) &h->h_counts, 3 * (size_t) channels * sizeof(uint32_t),
+                                            cudaHostAllocDefault);
+    if (e != cudaSuccess) {
+        dh::set_error("dh_decoder_create: %s", cudaGetErrorString(e));
+        dh_decoder_destroy(h);
+        return (int) e;
+    }
+    *out = h;
+    return DH_OK;
+}
+
+int dh_decoder_reserve(dh_decoder* h, size_t max_syms, uint8_t** d_buf, size_t* pitch) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_reserve: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    int rc = decoder_reserve(h, max_syms);
+    if (rc != DH_OK) return rc;
+    if (d_buf) *d_buf = h->d_sym + h->ops->carry_cap;
+    if (pitch) *pitch = h->sym_pitch;
+    return DH_OK;
+}
+
+int dh_decoder_set_slot_filter(dh_decoder* h, int channel, uint8_t filter) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_set_slot_filter: handle is NULL");
+    DH_REQUIRE(channel < (int) h->channels, DH_E_INVALID, "dh_decoder_set_slot_filter: channel out of range");
+    if (channel < 0) std::fill(h->h_slot_filter.begin(), h->h_slot_filter.end(), filter);
+    else h->h_slot_filter[channel] = filter;
+    h->filter_dirty = true;
+    return DH_OK;
+}
+
+int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, const uint32_t* d_nsym, size_t max_nsym,
+                       void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_process: handle is NULL");
+    DH_REQUIRE(d_nsym != nullptr, DH_E_INVALID, "dh_decoder_process: d_nsym is NULL");
+    if (max_nsym == 0) return DH_OK;
+    DH_REQUIRE(d_sym != nullptr, DH_E_INVALID, "dh_decoder_process: d_sym is NULL");
+    dh::DeviceGuard guard(h->device);
+    cudaStream_t st = (cudaStream_t) stream;
+    const bool zero_copy = h->d_sym && d_sym == h->d_sym + h->ops->carry_cap && sym_pitch == h->sym_pitch &&
+                           max_nsym <= h->max_syms;
+    if (!zero_copy) {
+        DH_REQUIRE(sym_pitch >= max_nsym, DH_E_INVALID, "dh_decoder_process: sym_pitch < max_nsym");
+        int rc = decoder_reserve(h, max_nsym);
+        if (rc != DH_OK) return rc;
+        DH_CUDA(cudaMemcpy2DAsync(h->d_sym + h->ops->carry_cap, h->sym_pitch, d_sym, sym_pitch, max_nsym, h->channels,
+                                  cudaMemcpyDeviceToDevice, st));
+    }
+    if (h->filter_dirty) {
+        DH_CUDA(cudaMemcpyAsync(h->d_slot_filter, h->h_slot_filter.data(), h->channels, cudaMemcpyHostToDevice, st));
+        DH_CUDA(cudaStreamSynchronize(st));   // the source vector may change right after this call
+        h->filter_dirty = false;
+    }
+    DecIo io;
+    io.sym = h->d_sym;
+    io.sym_pitch = h->sym_pitch;
+    io.nsym = d_nsym;
+    io.out = h->d_out;
+    io.out_len = h->d_counts;
+    io.ev = h->d_ev;
+    io.ev_len = h->d_counts + h->channels;
+    io.flags = h->d_counts + 2 * (size_t) h->channels;
+    io.out_cap = h->out_cap;
+    io.ev_cap = h->ev_cap;
+    io.carry_cap = h->ops->carry_cap;
+    io.channels = (int) h->channels;
+    return h->ops->launch(io, h->d_states, h->d_slot_filter, st);
+}
+
+int dh_decoder_collect(dh_decoder* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_collect: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    return decoder_collect(h, (cudaStream_t) stream);
+}
+
+int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len) {
+    DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_output: bad handle or channel");
+    if (data) *data = reinterpret_cast<const uint8_t*>(h->results[channel].bytes.data());
+    if (len) *len = h->results[channel].bytes.size();
+    return DH_OK;
+}
+
+int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len) {
+    DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_meta: bad handle or channel");
+    if (text) *text = h->results[channel].meta.data();
+    if (len) *len = h->results[channel].meta.size();
+    return DH_OK;
+}
+
+int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_totals: handle is NULL");
+    if (out_bytes) *out_bytes = h->total_bytes;
+    if (meta_bytes) *meta_bytes = h->total_meta;
+    return DH_OK;
+}
+
+int dh_decoder_clear(dh_decoder* h) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_clear: handle is NULL");
+    for (auto& r : h->results) {
+        r.bytes.clear();
+        r.meta.clear();
+    }
+    return DH_OK;
+}
+
+void dh_decoder_destroy(dh_decoder* h) {
+    if (!h) return;
+    dh::DeviceGuard guard(h->device);
+    cudaFree(h->d_states);
+    cudaFree(h->d_sym);
+    cudaFree(h->d_out);
+    cudaFree(h->d_ev);
+    cudaFree(h->d_counts);
+    cudaFree(h->d_slot_filter);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_out) cudaFreeHost(h->h_out);
+    if (h->h_ev) cudaFreeHost(h->h_ev);
+    for (auto* r : h->replay) delete r;
+    delete h;
+}
+
+}  // extern "C"

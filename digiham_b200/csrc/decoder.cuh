@@ -1,0 +1,98 @@
+// decoder.cuh — plumbing shared by the protocol decoder banks (DMR / YSF / POCSAG), sm_100a.
+//
+// A decoder bank replaces N instances of Digiham::Decoder (reference include/decoder.hpp:17-30,
+// src/lib/decoder.cpp:21-32): a phase state machine per channel that consumes demodulated symbols (one byte
+// each) and emits (a) a byte stream and (b) metadata updates.  On the GPU one warp owns one channel:
+//   * symbols live in per-channel rows with the unconsumed tail carried right-aligned in front of the column
+//     where the producer (K2) writes the next chunk, so the logical stream is contiguous;
+//   * output bytes are appended to per-channel rows, metadata leaves the GPU as compact 16-byte event records
+//     which the host replays into the reference's `key:value;...\n` lines (src/lib/meta.cpp:8-17).
+#pragma once
+#include "common.cuh"
+
+#include <string>
+#include <vector>
+
+namespace dh {
+
+struct DecEvent {
+    uint8_t kind;
+    uint8_t slot;
+    uint8_t a;
+    uint8_t b;
+    uint8_t data[12];
+};
+static_assert(sizeof(DecEvent) == 16, "event records are 16 bytes");
+
+constexpr uint32_t kFlagOutOverflow = 1u;
+constexpr uint32_t kFlagEventOverflow = 2u;
+
+struct DecIo {
+    uint8_t* sym;                 // [channels][sym_pitch]; new symbols start at column carry_cap
+    unsigned long long sym_pitch;
+    const uint32_t* nsym;         // [channels] symbols appended by the producer for this call
+    uint8_t* out;                 // [channels][out_cap]
+    uint32_t* out_len;            // [channels] bytes appended since the last collect
+    DecEvent* ev;                 // [channels][ev_cap]
+    uint32_t* ev_len;             // [channels]
+    uint32_t* flags;              // [channels] kFlag* bits
+    uint32_t out_cap;
+    uint32_t ev_cap;
+    int carry_cap;
+    int channels;
+};
+
+#ifdef __CUDACC__
+
+// Appends bytes / events of one channel; every lane of the owning warp holds the same counters.
+struct DecWriter {
+    uint8_t* out;
+    DecEvent* ev;
+    uint32_t out_len, ev_len, out_cap, ev_cap, flags;
+
+    __device__ __forceinline__ void event(int lane, uint8_t kind, uint8_t slot, uint8_t a = 0, uint8_t b = 0,
+                                          const uint8_t* data = nullptr, int ndata = 0) {
+        if (ev_len >= ev_cap) {
+            flags |= kFlagEventOverflow;
+            return;
+        }
+        if (lane == 0) {
+            DecEvent e;
+            e.kind = kind;
+            e.slot = slot;
+            e.a = a;
+            e.b = b;
+#pragma unroll
+            for (int i = 0; i < 12; i++) e.data[i] = (data != nullptr && i < ndata) ? data[i] : 0;
+            ev[ev_len] = e;
+        }
+        ev_len++;
+    }
+};
+
+// move the unconsumed tail [pos, T) of a symbol row right-aligned in front of column carry_cap (dst <= src)
+__device__ __forceinline__ void carry_symbols(uint8_t* row, int carry_cap, int carry_len, int pos, int T, int lane) {
+    const int keep = T - pos;
+    const uint8_t* src = row + (carry_cap - carry_len) + pos;
+    uint8_t* dst = row + carry_cap - keep;
+    if (dst == src) return;
+    for (int o = 0; o < keep; o += 32) {
+        const int idx = o + lane;
+        const uint8_t v = idx < keep ? src[idx] : 0;
+        __syncwarp();
+        if (idx < keep) dst[idx] = v;
+        __syncwarp();
+    }
+}
+
+__device__ __forceinline__ uint32_t parity32(uint32_t v) { return __popc(v) & 1u; }
+
+#endif  // __CUDACC__
+
+// Host side of a bank: per-channel accumulated results between dh_decoder_collect calls.
+struct ChannelResult {
+    std::string bytes;
+    std::string meta;
+};
+
+}  // namespace dh

@@ -39,3 +39,244 @@ def modulate(symbols, sps=10, n_samples=None, amplitude=0.5, levels=LEVELS4, ppm
 
 def random_symbols(n, levels=4, seed=0):
     return np.random.default_rng(seed).integers(0, levels, size=n).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Systematic block-code encoders.  For every code of the reference the check matrix is H = [A | I_r]
+# (identity in the low r bits), hence codeword = (data << r) | syndrome(data << r)  (SURVEY.md appendix A.0).
+_P = {
+    "hamming_7_4": (7, 4, ["101", "111", "110", "011"]),
+    "hamming_13_9": (13, 9, ["1111", "1110", "0111", "1010", "0101", "1011", "1100", "0110", "0011"]),
+    "hamming_15_11": (15, 11, ["1001", "1101", "1111", "1110", "0111", "1010", "0101", "1011", "1100", "0110", "0011"]),
+    "hamming_16_11": (16, 11, ["10011", "11010", "11111", "11100", "01110", "10101", "01011", "10110", "11001",
+                               "01101", "00111"]),
+    "qr_16_7": (16, 7, ["001001111", "100011110", "110110111", "111100010", "111001001", "011100101", "001110011"]),
+    "golay_20_8": (20, 8, ["001111011010", "110110011001", "011011001101", "001101100111", "110111000110",
+                           "101010010111", "100100111110", "100011101011"]),
+    "golay_24_12": (24, 12, ["110001110101", "011000111011", "111101101000", "011110110100", "001111011010",
+                             "110110011001", "011011001101", "001101100111", "110111000110", "101010010111",
+                             "100100111110", "100011101011"]),
+}
+
+
+def encode_block(code, data):
+    """data: k-bit integer (MSB = first data bit) -> n-bit systematic codeword."""
+    n, k, rows = _P[code]
+    r = n - k
+    parity = 0
+    for d in range(k):
+        if (data >> (k - 1 - d)) & 1:
+            parity ^= int(rows[d], 2)
+    return (data << r) | parity
+
+
+def bch_31_21_encode(data21):
+    """POCSAG BCH(31,21), generator x^10+x^9+x^8+x^6+x^5+x^3+1."""
+    poly = 0b11101101001
+    v = data21 << 10
+    for s in range(30, 9, -1):
+        if v & (1 << s):
+            v ^= poly << (s - 10)
+    return (data21 << 10) | v
+
+
+def _bits_to_dibits(bits):
+    bits = np.asarray(bits, dtype=np.uint8)
+    return (bits[0::2] << 1 | bits[1::2]).astype(np.uint8)
+
+
+def _int_to_bits(v, n):
+    return np.array([(v >> (n - 1 - i)) & 1 for i in range(n)], dtype=np.uint8)
+
+
+def _hex_to_dibits(h):
+    v = int(h, 16)
+    n = len(h) * 4
+    return _bits_to_dibits(_int_to_bits(v, n))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# DMR (ETSI TS 102 361-1) base-station frame generator.  Layout as the reference reads it
+# (src/dmr_decoder/dmr_phase.cpp:65-302, SURVEY.md appendix A.2): 144 dibits =
+#   CACH(12) | payload(54) | SYNC-or-EMB(24) | payload(54)
+DMR_SYNC = {
+    "bs_data": _hex_to_dibits("DFF57D75DF5D"),
+    "bs_voice": _hex_to_dibits("755FD7DF75F7"),
+    "ms_data": _hex_to_dibits("D5D7F77FD757"),
+    "ms_voice": _hex_to_dibits("7F7D5DD57DFD"),
+}
+DMR_DT_VOICE_LC, DMR_DT_TERMINATOR_LC, DMR_DT_CSBK, DMR_DT_RATE_34, DMR_DT_IDLE = 1, 2, 3, 8, 9
+
+
+def dmr_cach(slot, lcss, rng, busy=1):
+    tact4 = (busy << 3) | (slot << 2) | lcss
+    tact = encode_block("hamming_7_4", tact4)
+    bits = rng.integers(0, 2, size=24).astype(np.uint8)
+    for i, pos in enumerate([0, 4, 8, 12, 14, 18, 22]):
+        bits[pos] = (tact >> (6 - i)) & 1
+    return _bits_to_dibits(bits)
+
+
+def dmr_bptc_encode(info12):
+    """12 info bytes -> 196 transmitted bits (BPTC(196,96), reference src/dmr_decoder/bptc_196_96.c:12-56)."""
+    info_bits = np.unpackbits(np.asarray(info12, dtype=np.uint8))
+    m = np.zeros((13, 15), dtype=np.uint8)
+    m[0, 3:11] = info_bits[:8]
+    m[1:9, 0:11] = info_bits[8:].reshape(8, 11)
+    for r in range(9):
+        data = int("".join(str(b) for b in m[r, :11]), 2)
+        cw = encode_block("hamming_15_11", data)
+        m[r, :] = _int_to_bits(cw, 15)
+    for c in range(15):
+        data = int("".join(str(b) for b in m[:9, c]), 2)
+        cw = encode_block("hamming_13_9", data)
+        m[:, c] = _int_to_bits(cw, 13)
+    d = np.zeros(196, dtype=np.uint8)
+    d[1:] = m.reshape(-1)
+    t = np.zeros(196, dtype=np.uint8)
+    for i in range(196):
+        t[(i * 181) % 196] = d[i]
+    return t
+
+
+def dmr_slot_type(color_code, data_type):
+    return _int_to_bits(encode_block("golay_20_8", (color_code << 4) | data_type), 20)
+
+
+def dmr_data_burst(slot, data_type, info12, rng, color_code=1, sync="bs_data", lcss=0):
+    t = dmr_bptc_encode(info12)
+    st = dmr_slot_type(color_code, data_type)
+    f = np.zeros(144, dtype=np.uint8)
+    f[0:12] = dmr_cach(slot, lcss, rng)
+    f[12:61] = _bits_to_dibits(t[:98])
+    f[61:66] = _bits_to_dibits(st[:10])
+    f[66:90] = DMR_SYNC[sync]
+    f[90:95] = _bits_to_dibits(st[10:])
+    f[95:144] = _bits_to_dibits(t[98:])
+    return f
+
+
+def dmr_embedded_lc_fragments(lc9):
+    """9 LC bytes -> four 32-bit fragments (16 dibits each), reference src/dmr_decoder/embedded.cpp:37-89."""
+    lc9 = [int(b) for b in lc9]
+    bits = np.unpackbits(np.asarray(lc9, dtype=np.uint8))   # 72 bits
+    cs = sum(lc9) % 31
+    csbits = _int_to_bits(cs, 5)
+    rows = []
+    pos = 0
+    for r in range(7):
+        if r < 2:
+            data = bits[pos:pos + 11]
+            pos += 11
+        else:
+            data = np.concatenate([bits[pos:pos + 10], csbits[r - 2:r - 1]])
+            pos += 10
+        rows.append(encode_block("hamming_16_11", int("".join(str(b) for b in data), 2)))
+    parity = 0
+    for r in rows:
+        parity ^= r
+    rows.append(parity)
+    data = np.zeros(16, dtype=np.uint8)
+    for i in range(16):
+        b = 0
+        for k in range(8):
+            b |= ((rows[k] >> (15 - i)) & 1) << (7 - k)
+        data[i] = b
+    return [_bits_to_dibits(np.unpackbits(data[4 * q:4 * q + 4])) for q in range(4)]
+
+
+def dmr_voice_burst(slot, rng, sync="bs_voice", emb=None, fragment=None, lcss_cach=0):
+    """emb = (color_code, pi, lcss) for superframe bursts B..F, None for burst A (voice sync)."""
+    f = np.zeros(144, dtype=np.uint8)
+    f[0:12] = dmr_cach(slot, lcss_cach, rng)
+    f[12:66] = rng.integers(0, 4, size=54)
+    f[90:144] = rng.integers(0, 4, size=54)
+    if emb is None:
+        f[66:90] = DMR_SYNC[sync]
+    else:
+        cc, pi, lcss = emb
+        e = _int_to_bits(encode_block("qr_16_7", (cc << 3) | (pi << 2) | lcss), 16)
+        f[66:70] = _bits_to_dibits(e[:8])
+        f[70:86] = fragment if fragment is not None else rng.integers(0, 4, size=16)
+        f[86:90] = _bits_to_dibits(e[8:])
+    return f
+
+
+def dmr_full_lc(opcode, target, source, fid=0, options=0, rng=None):
+    lc = [opcode & 0x3F, fid, options, (target >> 16) & 0xFF, (target >> 8) & 0xFF, target & 0xFF,
+          (source >> 16) & 0xFF, (source >> 8) & 0xFF, source & 0xFF]
+    tail = list(rng.integers(0, 256, size=3)) if rng is not None else [0, 0, 0]
+    return lc + [int(t) for t in tail]
+
+
+def dmr_slot_script(rng, kind):
+    """A list of burst makers for one TDMA slot.  kind: 'voice', 'data', 'idle', 'mixed'."""
+    bursts = []
+
+    def voice_call(n_super, target, source, group=True, with_ta=False, with_gps=False):
+        opcode = 0 if group else 3
+        lc = dmr_full_lc(opcode, target, source, rng=rng)
+        bursts.append(("data", DMR_DT_VOICE_LC, lc))
+        emb_lcs = [lc[:9]]
+        if with_ta:
+            # talker alias header + block 1 (reference src/dmr_decoder/talkeralias.cpp:58-144): the 7 payload
+            # bytes start at LC byte 2; header byte = format(2) | length(5) | 1 spare bit
+            name = b"B200 TESTER"
+            hdr = [4, 0, (1 << 6) | (len(name) << 1)] + list(name[:6])             # 8-bit format
+            emb_lcs.append(hdr[:9])
+            rest = list(name[6:13])
+            blk1 = [5, 0] + rest + [0] * (7 - len(rest))
+            emb_lcs.append(blk1[:9])
+        if with_gps:
+            emb_lcs.append([8, 0, 0x01, 0x12, 0x34, 0x56, 0x23, 0x45, 0x67])
+        for s in range(n_super):
+            frags = dmr_embedded_lc_fragments(emb_lcs[s % len(emb_lcs)])
+            bursts.append(("voice", None, None))
+            for q, lcss in enumerate([1, 3, 3, 2]):
+                bursts.append(("voice", (1, 0, lcss), frags[q]))
+            bursts.append(("voice", (1, 0, 0), None))
+        bursts.append(("data", DMR_DT_TERMINATOR_LC, lc))
+
+    if kind == "idle":
+        for _ in range(40):
+            bursts.append(("data", DMR_DT_IDLE, list(rng.integers(0, 256, size=12))))
+    elif kind == "data":
+        for i in range(40):
+            dt = [DMR_DT_CSBK, DMR_DT_IDLE, DMR_DT_RATE_34, 6, 7][i % 5]
+            bursts.append(("data", dt, list(rng.integers(0, 256, size=12))))
+    elif kind == "voice":
+        voice_call(6, int(rng.integers(1, 1 << 24)), int(rng.integers(1, 1 << 24)), group=True, with_ta=True,
+                   with_gps=True)
+    else:
+        for _ in range(3):
+            bursts.append(("data", DMR_DT_IDLE, list(rng.integers(0, 256, size=12))))
+        voice_call(2, int(rng.integers(1, 1 << 24)), int(rng.integers(1, 1 << 24)), group=bool(rng.integers(0, 2)))
+        for _ in range(4):
+            bursts.append(("data", DMR_DT_CSBK, list(rng.integers(0, 256, size=12))))
+        voice_call(3, int(rng.integers(1, 1 << 24)), int(rng.integers(1, 1 << 24)), group=False, with_ta=True)
+    return bursts
+
+
+def dmr_symbols(n_frames, seed=0, kinds=("voice", "mixed"), lead_in=None, symbol_errors=0.0):
+    """Dibit stream of a DMR base-station carrier: the two slots alternate, each following its own script.
+    lead_in random dibits precede the first frame; symbol_errors is the per-dibit probability of a random error."""
+    rng = np.random.default_rng(seed)
+    scripts = [dmr_slot_script(rng, kinds[0]), dmr_slot_script(rng, kinds[1])]
+    idx = [0, 0]
+    if lead_in is None:
+        lead_in = int(rng.integers(0, 200))
+    out = [rng.integers(0, 4, size=lead_in).astype(np.uint8)]
+    for fno in range(n_frames):
+        slot = fno & 1
+        sc = scripts[slot]
+        kind, a, b = sc[idx[slot] % len(sc)]
+        idx[slot] += 1
+        if kind == "data":
+            out.append(dmr_data_burst(slot, a, b, rng))
+        else:
+            out.append(dmr_voice_burst(slot, rng, emb=a, fragment=b))
+    s = np.concatenate(out)
+    if symbol_errors > 0:
+        hit = rng.random(s.size) < symbol_errors
+        s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
+    return s

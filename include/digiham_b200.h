@@ -22,6 +22,8 @@
  *   dh_demod_*    Digiham::Fsk::GfskDemodulator(sps)                               include/gfsk_demodulator.hpp:12-33
  *                 Digiham::Fsk::FskDemodulator(sps, invert)                        include/fsk_demodulator.hpp:12-33
  *                 canProcess()/process()              src/gfsk_demodulator/gfsk_demodulator.cpp:18-122, src/fsk_demodulator/fsk_demodulator.cpp:19-112
+ *   dh_decoder_*  Digiham::Decoder::{canProcess,process,setMetaWriter}             include/decoder.hpp:17-30, src/lib/decoder.cpp:21-47
+ *                 Digiham::Dmr::Decoder::{Decoder,setSlotFilter}                   include/dmr_decoder.hpp:9-17, src/dmr_decoder/dmr_phase.cpp:35-345
  */
 #ifndef DIGIHAM_B200_H
 #define DIGIHAM_B200_H
@@ -104,6 +106,44 @@ DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, siz
                             size_t sym_pitch, uint32_t* d_nsym, void* stream);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Protocol decoder bank — N x Digiham::Dmr::Decoder / Ysf::Decoder / Pocsag::Decoder.
+ *
+ * Input: one byte per demodulated symbol (0..3 for DMR/YSF, 0/1 for POCSAG), exactly what the demodulator
+ * banks emit.  Output per channel, in stream order:
+ *   - the decoder's byte stream (DMR: 27-byte voice frames, src/dmr_decoder/dmr_phase.cpp:207-227);
+ *   - the metadata lines a FileMetaWriter with the default StringSerializer would have written
+ *     (`protocol:DMR;slot:0;...\n`, src/lib/meta.cpp:8-17,42-46).
+ * Results accumulate on the device; dh_decoder_collect moves them into host buffers owned by the bank.
+ */
+typedef struct dh_decoder dh_decoder;
+
+#define DH_PROTO_DMR 0
+#define DH_PROTO_YSF 1
+#define DH_PROTO_POCSAG 2
+
+DH_API int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto);
+/* Zero-copy input: device address (row of channel 0) and pitch where a producer such as dh_demod_process should
+ * write up to max_syms symbols per channel for the next dh_decoder_process call. */
+DH_API int dh_decoder_reserve(dh_decoder* h, size_t max_syms, uint8_t** d_buf, size_t* pitch);
+/* Dmr::Decoder::setSlotFilter (include/dmr_decoder.hpp:12): bit 0 = slot 0, bit 1 = slot 1; channel < 0 = all.
+ * Takes effect at the next dh_decoder_process call. */
+DH_API int dh_decoder_set_slot_filter(dh_decoder* h, int channel, uint8_t filter);
+/* Consumes d_nsym[c] (<= max_nsym) new symbols of every channel c (d_nsym is a DEVICE array). */
+DH_API int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, const uint32_t* d_nsym,
+                              size_t max_nsym, void* stream);
+/* Synchronises with `stream`, copies everything produced since the last collect to the host and appends it to
+ * the per-channel host buffers.  Must be called at least once every 2 process calls. */
+DH_API int dh_decoder_collect(dh_decoder* h, void* stream);
+/* Host views of one channel's accumulated results; valid until the next collect / clear / destroy. */
+DH_API int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len);
+DH_API int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len);
+/* totals over all channels since creation */
+DH_API int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes);
+/* drops the accumulated host results */
+DH_API int dh_decoder_clear(dh_decoder* h);
+DH_API void dh_decoder_destroy(dh_decoder* h);
 
 #ifdef __cplusplus
 }

@@ -145,10 +145,17 @@ def build_lut(n, rows, t, mode):
 
 
 def c_array(ctype, name, vals, fmt, per_line=8):
-    lines = ["static const %s %s[%d] = {" % (ctype, name, len(vals))]
+    """Emits `#define <NAME>_INIT { ... }` (usable as a __constant__ initialiser) and, unless
+    DH_TABLES_NO_HOST_ARRAYS is defined, a static host array initialised from it."""
+    macro = name.upper() + "_INIT"
+    lines = ["#define %s { \\" % macro]
     for i in range(0, len(vals), per_line):
-        lines.append("    " + ", ".join(fmt % v for v in vals[i:i + per_line]) + ",")
-    lines.append("};")
+        lines.append("    " + ", ".join(fmt % v for v in vals[i:i + per_line]) + ", \\")
+    lines.append("}")
+    lines.append("#define %s_LEN %d" % (name.upper(), len(vals)))
+    lines.append("#ifndef DH_TABLES_NO_HOST_ARRAYS")
+    lines.append("static const %s %s[%d] = %s;" % (ctype, name, len(vals), macro))
+    lines.append("#endif")
     return "\n".join(lines)
 
 
