@@ -15,6 +15,7 @@ from ._capi import (  # noqa: F401
     RrcBank,
     DemodBank,
     DecoderBank,
+    Pipe,
     PROTO_DMR,
     PROTO_YSF,
     PROTO_POCSAG,
@@ -22,4 +23,4 @@ from ._capi import (  # noqa: F401
     RRC_NARROW,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]

@@ -71,6 +71,21 @@ def lib():
     L.dh_decoder_clear.argtypes = [ctypes.c_void_p]
     L.dh_decoder_destroy.argtypes = [ctypes.c_void_p]
     L.dh_decoder_destroy.restype = None
+    L.dh_pipe_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_size_t]
+    L.dh_pipe_process_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                         ctypes.c_void_p]
+    L.dh_pipe_process_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
+                                       ctypes.c_void_p]
+    L.dh_pipe_host_pitch.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_host_pitch.restype = ctypes.c_size_t
+    L.dh_pipe_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_pipe_decoder.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_decoder.restype = ctypes.c_void_p
+    L.dh_pipe_last_symbols.argtypes = [ctypes.c_void_p, c_void_pp, ctypes.POINTER(ctypes.c_size_t), c_void_pp]
+    L.dh_pipe_read_symbols.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
+                                       ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_destroy.restype = None
     _lib = L
     return L
 
@@ -254,6 +269,70 @@ class DecoderBank:
     def close(self):
         if self._h:
             lib().dh_decoder_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Pipe:
+    """rrc_filter | gfsk_demodulator | <proto>_decoder for N channels (reference examples/*-decoder.sh)."""
+
+    def __init__(self, channels, proto=PROTO_DMR, max_chunk=48000, device="cuda:0"):
+        self._h = ctypes.c_void_p()
+        self.channels = int(channels)
+        self.proto = proto
+        self.max_chunk = int(max_chunk)
+        self.device = torch.device(device)
+        check(lib().dh_pipe_create(ctypes.byref(self._h), _dev_index(device), self.channels, proto, self.max_chunk))
+        # a non-owning view of the pipe's decoder bank
+        self.decoder = DecoderBank.__new__(DecoderBank)
+        self.decoder._h = ctypes.c_void_p(lib().dh_pipe_decoder(self._h))
+        self.decoder.channels = self.channels
+        self.decoder.proto = proto
+        self.decoder.device = self.device
+        self.decoder.close = lambda: None
+
+    @property
+    def host_pitch(self):
+        return lib().dh_pipe_host_pitch(self._h)
+
+    def process(self, x, n=None, stream=None):
+        """x: float32 tensor [channels, pitch]; CUDA tensors are consumed in place, CPU tensors are copied."""
+        assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] == self.channels and x.stride(1) == 1
+        if n is None:
+            n = x.shape[1]
+        if x.is_cuda:
+            check(lib().dh_pipe_process_device(self._h, x.data_ptr(), x.stride(0), n, _stream_ptr(stream)))
+        else:
+            check(lib().dh_pipe_process_host(self._h, x.data_ptr(), x.stride(0), n, _stream_ptr(stream)))
+
+    def collect(self, stream=None):
+        check(lib().dh_pipe_collect(self._h, _stream_ptr(stream)))
+
+    def last_symbols(self, channel):
+        """numpy uint8 array: the symbols the demodulator emitted for `channel` in the last process call."""
+        import numpy as np
+        buf = np.empty(self.max_chunk // 4 + 4096, dtype=np.uint8)
+        n = ctypes.c_size_t()
+        check(lib().dh_pipe_read_symbols(self._h, channel, buf.ctypes.data, buf.size, ctypes.byref(n)))
+        return buf[:n.value].copy()
+
+    def output(self, channel):
+        return self.decoder.output(channel)
+
+    def meta(self, channel):
+        return self.decoder.meta(channel)
+
+    def totals(self):
+        return self.decoder.totals()
+
+    def close(self):
+        if self._h:
+            lib().dh_pipe_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

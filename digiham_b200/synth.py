@@ -280,3 +280,77 @@ def dmr_symbols(n_frames, seed=0, kinds=("voice", "mixed"), lead_in=None, symbol
         hit = rng.random(s.size) < symbol_errors
         s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Batched modulation with torch (harness glue): the same rectangular-hold model as modulate(), vectorised over
+# channels and runnable on the GPU so that bench-sized inputs (thousands of channels) are built in seconds.
+def modulate_batch(symbols, n_samples, sps=10, levels=LEVELS4, amplitude=0.5, ppm=0.0, phase=0.0, snr_db=None,
+                   dc=0.0, seed=0, device="cpu", pitch=None, chunk_channels=512):
+    """symbols: uint8 array [C, S].  Per-channel scalars may be arrays of length C (snr_db: inf = no noise).
+    Returns a float32 torch tensor [C, pitch] on `device` (pitch >= n_samples, padding zero)."""
+    import torch
+    symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+    C, S = symbols.shape
+    if pitch is None:
+        pitch = (n_samples + 3) & ~3
+
+    def vec(v):
+        return torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=np.float64), (C,)).copy(), device=device)
+
+    amp, ppm_t, ph, dc_t = vec(amplitude), vec(ppm), vec(phase), vec(dc)
+    snr = vec(np.inf if snr_db is None else snr_db)
+    lev = torch.as_tensor(np.asarray(levels, dtype=np.float64), device=device)
+    p_sig = float(np.mean(np.asarray(levels) ** 2))
+    out = torch.zeros((C, pitch), dtype=torch.float32, device=device)
+    gen = torch.Generator(device=device)
+    gen.manual_seed(int(seed))
+    t = torch.arange(n_samples, dtype=torch.float64, device=device)
+    sym_t = torch.as_tensor(symbols, device=device)
+    for c0 in range(0, C, chunk_channels):
+        c1 = min(C, c0 + chunk_channels)
+        idx = torch.floor((t[None, :] + ph[c0:c1, None]) * (1.0 + ppm_t[c0:c1, None] * 1e-6) / sps).to(torch.int64)
+        idx.clamp_(0, S - 1)
+        x = lev[torch.gather(sym_t[c0:c1], 1, idx).to(torch.int64)] * amp[c0:c1, None] + dc_t[c0:c1, None]
+        sigma = torch.sqrt(p_sig * amp[c0:c1] ** 2 / torch.pow(10.0, snr[c0:c1] / 10.0))
+        sigma = torch.where(torch.isfinite(snr[c0:c1]), sigma, torch.zeros_like(sigma))
+        noise = torch.randn((c1 - c0, n_samples), dtype=torch.float32, device=device, generator=gen)
+        x = x + noise.to(torch.float64) * sigma[:, None]
+        out[c0:c1, :n_samples] = x.clamp_(-1.0, 1.0).to(torch.float32)
+    return out
+
+
+def dmr_channel_bank(channels, n_samples, seed=0, device="cpu", pool=48, noise_fraction=0.1):
+    """Synthetic workload of SURVEY.md §8d C2: `channels` 48 kHz channels carrying DMR base-station traffic
+    (voice superframes, LC headers/terminators, idle/CSBK/rate-3/4 bursts, valid FEC everywhere), with per-channel
+    start phase, amplitude, DC offset, AWGN (SNR from {inf, 20, 12, 6} dB), sampling-clock offset
+    (0, +-20, +-50 ppm) and ~10 % channels of pure noise.  Returns (float32 tensor [channels, pitch], info dict)."""
+    rng = np.random.default_rng(seed)
+    sps = 10
+    n_sym = n_samples // sps + 300
+    frames = n_sym // 144 + 2
+    kinds = [("voice", "mixed"), ("mixed", "voice"), ("idle", "voice"), ("data", "mixed"), ("voice", "voice"),
+             ("mixed", "data"), ("voice", "idle"), ("mixed", "mixed")]
+    base = []
+    for k in range(min(pool, channels)):
+        s = dmr_symbols(frames, seed=seed * 7919 + k, kinds=kinds[k % len(kinds)], lead_in=0)
+        base.append(s[:frames * 144])
+    base = np.stack(base)
+    S = base.shape[1]
+    symbols = np.empty((channels, S), dtype=np.uint8)
+    shifts = rng.integers(0, S, size=channels)
+    noise_only = rng.random(channels) < noise_fraction
+    for c in range(channels):
+        if noise_only[c]:
+            symbols[c] = rng.integers(0, 4, size=S)
+        else:
+            symbols[c] = np.roll(base[c % base.shape[0]], int(shifts[c]))
+    snr = rng.choice([np.inf, 20.0, 12.0, 6.0], size=channels)
+    ppm = rng.choice([0.0, 20.0, -20.0, 50.0, -50.0], size=channels)
+    phase = rng.integers(0, 1440, size=channels).astype(np.float64)
+    amp = rng.choice([0.25, 0.5, 0.8], size=channels)
+    dc = rng.choice([0.0, 0.02, -0.05], size=channels)
+    x = modulate_batch(symbols, n_samples, sps=sps, amplitude=amp, ppm=ppm, phase=phase, snr_db=snr, dc=dc,
+                       seed=seed + 1, device=device)
+    info = {"noise_only": noise_only, "snr_db": snr, "ppm": ppm}
+    return x, info

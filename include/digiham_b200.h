@@ -145,6 +145,34 @@ DH_API int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_
 DH_API int dh_decoder_clear(dh_decoder* h);
 DH_API void dh_decoder_destroy(dh_decoder* h);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Whole pipe of one protocol for N channels, wired like the reference's example scripts:
+ *   DH_PROTO_DMR / DH_PROTO_YSF : rrc_filter | gfsk_demodulator (sps 10) | {dmr,ysf}_decoder
+ *                                 (examples/dmr-decoder.sh:19-23, examples/ysf-decoder.sh:19-23)
+ *   DH_PROTO_POCSAG             : fsk_demodulator -i -s 40 | pocsag_decoder   (examples/pocsag-decoder.sh:19-21)
+ * Input is what the first module of those pipes reads: 48 kHz float32 FM-discriminator audio, one row per
+ * channel.  The stages hand their blocks over in device memory without copies.
+ */
+typedef struct dh_pipe dh_pipe;
+
+/* max_chunk: the largest n a process call will pass */
+DH_API int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size_t max_chunk);
+/* n samples per channel from DEVICE memory (16-byte aligned, pitch % 4 == 0, pitch >= n rounded up to 4) */
+DH_API int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream);
+/* n samples per channel from HOST memory (pinned memory makes the copy asynchronous); the host-to-device copy
+ * is part of the call.  A pitch of dh_pipe_host_pitch() allows one contiguous transfer. */
+DH_API int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream);
+DH_API size_t dh_pipe_host_pitch(const dh_pipe* h);
+/* same contract as dh_decoder_collect */
+DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
+/* the decoder bank of the pipe: use dh_decoder_output / _meta / _totals / _clear / _set_slot_filter on it */
+DH_API dh_decoder* dh_pipe_decoder(dh_pipe* h);
+/* device views of the symbols the demodulator produced in the LAST process call (parity artefact) */
+DH_API int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, const uint32_t** d_nsym);
+/* synchronous host copy of one channel's symbols of the last process call (test / debug helper) */
+DH_API int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t cap, size_t* count);
+DH_API void dh_pipe_destroy(dh_pipe* h);
+
 #ifdef __cplusplus
 }
 #endif
