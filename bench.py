@@ -1,0 +1,312 @@
+#!/usr/bin/env python3
+"""bench.py — Msamples/s through RRC -> GFSK demod -> DMR decoder for N x 4096 synthetic 48 kHz channels.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line on rank 0.
+  * a step = one pass of the hot path over one batch: 4096 channels x 48000 samples (1 s of signal) per GPU
+    (BASELINE.json configs[1]); the per-channel streams continue across steps (state is carried);
+  * `value`   : whole-job Msamples/s with the batch resident in HBM, timed with CUDA events on the launching
+                stream over exactly K steps, max over ranks;
+  * `e2e`     : the same metric through the C ABI with HOST buffers: pinned host -> device copy of every batch,
+                the three kernels, device -> host read of the decoded frames + metadata events and their replay;
+  * `roofline`: the dominant kernel (K1, the RRC FIR): algorithmic bytes (8 B/sample) / its live CUDA-event time;
+  * `cpu_baseline` (rank 0, N = 1): the reference's own CPU modules (oracle/_ref, compiled from the unmodified
+                reference sources) on a bounded sample of the same batch, all host cores.
+`--impl reference` times only that CPU arm, same metric/config.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CHANNELS_PER_GPU = 4096
+SAMPLES_PER_STEP = 48000
+METRIC = "Msamples/s RRC->GFSK->DMR pipe"
+ALGO_BYTES_PER_SAMPLE_K1 = 8.0       # K1 stand-alone: 4 B in + 4 B out
+ALGO_BYTES_PER_SAMPLE_PIPE = 4.119   # fused-pipe figure, reported for context
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed regions (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                smax.append(float(r[2]))
+                for k, nme in enumerate(names):
+                    if r[5 + k].lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, x_host_rows, cores):
+    """Times the reference CPU modules (or the port when the compiled reference is absent) on host cores.
+    x_host_rows: float32 numpy [channels, n].  Returns (Msamples/s, kind, sample description, seconds/step)."""
+    import oracle_lib
+    orc = oracle_lib.best()
+    nch, n = x_host_rows.shape
+    times = []
+    for it in range(args.warmup_ref + args.steps_ref):
+        t0 = time.perf_counter()
+        orc.pipe_batch(oracle_lib.PROTO_DMR, x_host_rows, threads=cores, chunk=4096)
+        dt = time.perf_counter() - t0
+        if it >= args.warmup_ref:
+            times.append(dt)
+    sec = sum(times) / len(times)
+    return nch * n / sec / 1e6, orc.kind, "%d channels x %d samples per step, %d step(s)" % (nch, n, len(times)), sec
+
+
+def build_host_sample(channels, n, seed):
+    """CPU-side generation of a bounded sample of the workload (used by --impl reference on a box whose GPU arm
+    is not running): same generator, same seed, first `channels` channels."""
+    from digiham_b200 import synth
+    x, _ = synth.dmr_channel_bank(channels, n, seed=seed, device="cpu")
+    return x[:, :n].contiguous().numpy()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
+    ap.add_argument("--samples", type=int, default=SAMPLES_PER_STEP, help="samples per channel per step")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    cores = os.cpu_count() or 1
+    config = {"workload": "%d ch/GPU x %d samples/step synthetic 48 kHz 4-FSK DMR (BASELINE configs[1]): "
+                          "WideRrcFilter -> GfskDemodulator(10) -> Dmr::Decoder" % (args.channels, args.samples),
+              "channels_per_gpu": args.channels, "samples_per_channel_per_step": args.samples,
+              "l2": "inputs larger than L2 (%.0f MB/step/GPU)" % (args.channels * args.samples * 4 / 1e6),
+              "sharding": "contiguous channel ranges per rank, no data-path collective"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample: enough channels for a few seconds of work on all cores
+        args.warmup_ref, args.steps_ref = min(args.warmup, 1), max(1, min(args.steps, 3))
+        nch = min(args.channels, 64 * cores)
+        x = build_host_sample(nch, args.samples, seed=1234)
+        val, kind, sample, sec = reference_arm(args, x, cores)
+        line = {"metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps_ref,
+                "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
+                "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
+                "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+    import digiham_b200 as dh
+    from digiham_b200 import synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the CUDA path is the only path (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    C, L = args.channels, args.samples
+    x, _ = synth.dmr_channel_bank(C, L, seed=1234 + rank, device=dev)      # [C, pitch] float32 in HBM
+    pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=L, device=dev)
+    stream = torch.cuda.current_stream()
+
+    sampler = ClockSampler(local_rank)
+    # ---- kernel-level arm: batch resident in HBM ---------------------------------------------------------------
+    for _ in range(args.warmup):
+        pipe.process(x, n=L)
+        pipe.decoder.discard()
+    torch.cuda.synchronize()
+    pipe.set_profiling(True)
+    launches0 = pipe.launch_count
+    barrier()
+    torch.cuda.synchronize()
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        pipe.process(x, n=L)
+        pipe.decoder.discard()       # results stay in HBM; only the device-side counters are reset
+    e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    stage_ms, calls = pipe.stage_times()
+    pipe.set_profiling(False)
+    launches = pipe.launch_count - launches0
+    if world > 1:
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * C * L / (ms_step * 1e-3) / 1e6
+
+    # ---- end-to-end arm: host buffers through the C ABI --------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        pitch = pipe.host_pitch
+        xh = torch.empty((C, pitch), dtype=torch.float32).pin_memory()
+        xh.copy_(x[:, :pitch] if x.shape[1] >= pitch else torch.nn.functional.pad(x, (0, pitch - x.shape[1])))
+        _, d2h0 = pipe.decoder.stats()
+        for _ in range(min(args.warmup, 3)):
+            pipe.process(xh, n=L)
+            pipe.collect()
+            pipe.decoder.clear()
+        _, d2h0 = pipe.decoder.stats()
+        k_e2e = args.steps
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(k_e2e):
+            pipe.process(xh, n=L)       # H2D copy + K1 + K2 + decoder kernel
+            pipe.collect()              # D2H of frames/events + host metadata replay (synchronises)
+            pipe.decoder.clear()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        _, d2h1 = pipe.decoder.stats()
+        e2e = {"value": world * C * L * k_e2e / dt / 1e6, "unit": "Msamples/s",
+               "h2d_bytes_per_step": C * pitch * 4, "d2h_bytes_per_step": (d2h1 - d2h0) // k_e2e,
+               "steps": k_e2e, "ms_per_step": dt / k_e2e * 1e3,
+               "path": "dh_pipe_process_host (pinned H2D) + dh_pipe_collect (D2H + metadata replay) per step"}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (K1) ------------------------------------------------------------------
+    peak, peak_src = peaks()
+    k1_ms = stage_ms[0] / max(1, calls)
+    achieved = C * L * ALGO_BYTES_PER_SAMPLE_K1 / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        if tj.get("channels") == C and tj.get("samples") == L:
+            traffic = tj.get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "kernel": "rrc_fir_kernel<80> (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_K1,
+                "ms_per_launch": k1_ms,
+                "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / max(1, calls),
+                                      "k3_k4_dmr": stage_ms[2] / max(1, calls)},
+                "fp32_issue_bound": {"note": "K1 executes 162 separately rounded fp32 ops/sample (no FMA, bit-exact); "
+                                             "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
+                                     "fp32_ops_per_s": C * L * 162 / (k1_ms * 1e-3) if k1_ms > 0 else None,
+                                     "peak_fp32_lane_ops_per_s_at_max_clock": 148 * 128 * 1.965e9},
+                "pipe_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_PIPE,
+                "pipe_frac_of_hbm": value * 1e6 / world * ALGO_BYTES_PER_SAMPLE_PIPE / 1e9 / peak}
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            import oracle_lib
+            orc = oracle_lib.best()
+            probe = x[:cores, :L].cpu().numpy()
+            t0 = time.perf_counter()
+            orc.pipe_batch(oracle_lib.PROTO_DMR, probe, threads=cores, chunk=4096)
+            per_ch = (time.perf_counter() - t0) / 1.0            # seconds for `cores` channels in parallel
+            nch = int(max(cores, min(C, cores * max(1.0, args.cpu_seconds / max(per_ch, 1e-3)))))
+            xs = x[:nch, :L].cpu().numpy()
+            t0 = time.perf_counter()
+            _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, xs, threads=cores, chunk=4096)
+            dt = time.perf_counter() - t0
+            cpu = {"value": nch * L / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": orc.kind,
+                   "sample": "first %d of %d channels x %d samples (one step's batch), %.1f s" % (nch, C, L, dt)}
+            # the same sample doubles as an in-run parity check of the GPU path
+            chk = dh.Pipe(nch, dh.PROTO_DMR, max_chunk=L, device=dev)
+            chk.process(x[:nch], n=L)
+            chk.collect()
+            ok = all(chk.output(c) == outs[c].tobytes() and chk.meta(c) == metas[c] for c in range(nch))
+            cpu["gpu_matches_cpu_on_sample"] = bool(ok)
+            chk.close()
+        except Exception as ex:   # the checker is optional for the measurement itself
+            cpu = {"value": None, "unit": "Msamples/s", "cores": cores, "kind": "unavailable", "sample": str(ex)}
+
+    line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -84,6 +84,12 @@ def lib():
     L.dh_pipe_last_symbols.argtypes = [ctypes.c_void_p, c_void_pp, ctypes.POINTER(ctypes.c_size_t), c_void_pp]
     L.dh_pipe_read_symbols.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                        ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_pipe_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dh_pipe_stage_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
+    L.dh_pipe_launch_count.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_launch_count.restype = ctypes.c_uint64
+    L.dh_decoder_stats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    L.dh_decoder_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
     L.dh_pipe_destroy.restype = None
     _lib = L
@@ -263,6 +269,15 @@ class DecoderBank:
         check(lib().dh_decoder_totals(self._h, ctypes.byref(a), ctypes.byref(b)))
         return a.value, b.value
 
+    def stats(self):
+        """(events replayed, bytes copied device->host) since creation."""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib().dh_decoder_stats(self._h, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
+    def discard(self, stream=None):
+        check(lib().dh_decoder_discard(self._h, _stream_ptr(stream)))
+
     def clear(self):
         check(lib().dh_decoder_clear(self._h))
 
@@ -312,6 +327,20 @@ class Pipe:
 
     def collect(self, stream=None):
         check(lib().dh_pipe_collect(self._h, _stream_ptr(stream)))
+
+    def set_profiling(self, enable):
+        check(lib().dh_pipe_set_profiling(self._h, int(enable)))
+
+    def stage_times(self):
+        """([ms_rrc, ms_demod, ms_decoder] summed, calls) since the previous query (synchronises)."""
+        ms = (ctypes.c_double * 3)()
+        calls = ctypes.c_uint64()
+        check(lib().dh_pipe_stage_times(self._h, ms, ctypes.byref(calls)))
+        return [ms[0], ms[1], ms[2]], calls.value
+
+    @property
+    def launch_count(self):
+        return lib().dh_pipe_launch_count(self._h)
 
     def last_symbols(self, channel):
         """numpy uint8 array: the symbols the demodulator emitted for `channel` in the last process call."""

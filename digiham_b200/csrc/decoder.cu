@@ -45,6 +45,8 @@ struct dh_decoder {
     std::vector<dh::MetaReplay*> replay;
     uint64_t total_bytes = 0;
     uint64_t total_meta = 0;
+    uint64_t total_events = 0;
+    uint64_t total_d2h = 0;   // bytes copied device->host by collect
 };
 
 namespace {
@@ -99,6 +101,7 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
     const uint32_t n = h->channels;
     DH_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     DH_CUDA(cudaStreamSynchronize(st));
+    h->total_d2h += 3 * (uint64_t) n * sizeof(uint32_t);
     const uint32_t* out_len = h->h_counts;
     const uint32_t* ev_len = h->h_counts + n;
     const uint32_t* flags = h->h_counts + 2 * (size_t) n;
@@ -112,6 +115,7 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
         int rc = grow_pinned((void**) &h->h_out, &h->h_out_bytes, (size_t) n * max_out);
         if (rc != DH_OK) return rc;
         DH_CUDA(cudaMemcpy2DAsync(h->h_out, max_out, h->d_out, h->out_cap, max_out, n, cudaMemcpyDeviceToHost, st));
+        h->total_d2h += (uint64_t) n * max_out;
     }
     if (max_ev) {
         const size_t w = (size_t) max_ev * sizeof(DecEvent);
@@ -119,6 +123,7 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
         if (rc != DH_OK) return rc;
         DH_CUDA(cudaMemcpy2DAsync(h->h_ev, w, h->d_ev, (size_t) h->ev_cap * sizeof(DecEvent), w, n,
                                   cudaMemcpyDeviceToHost, st));
+        h->total_d2h += (uint64_t) n * w;
     }
     DH_CUDA(cudaMemsetAsync(h->d_counts, 0, 3 * (size_t) n * sizeof(uint32_t), st));
     DH_CUDA(cudaStreamSynchronize(st));
@@ -128,6 +133,7 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
             r.bytes.append(reinterpret_cast<const char*>(h->h_out + (size_t) c * max_out), out_len[c]);
             h->total_bytes += out_len[c];
         }
+        h->total_events += ev_len[c];
         if (ev_len[c] && h->replay[c]) {
             const size_t before = r.meta.size();
             h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
@@ -273,6 +279,21 @@ int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes) 
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_totals: handle is NULL");
     if (out_bytes) *out_bytes = h->total_bytes;
     if (meta_bytes) *meta_bytes = h->total_meta;
+    return DH_OK;
+}
+
+int dh_decoder_stats(dh_decoder* h, uint64_t* events, uint64_t* d2h_bytes) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_stats: handle is NULL");
+    if (events) *events = h->total_events;
+    if (d2h_bytes) *d2h_bytes = h->total_d2h;
+    return DH_OK;
+}
+
+int dh_decoder_discard(dh_decoder* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_discard: handle is NULL");
+    if (!h->d_counts) return DH_OK;
+    dh::DeviceGuard guard(h->device);
+    DH_CUDA(cudaMemsetAsync(h->d_counts, 0, 3 * (size_t) h->channels * sizeof(uint32_t), (cudaStream_t) stream));
     return DH_OK;
 }
 

@@ -10,6 +10,7 @@
 #include "common.cuh"
 
 #include <new>
+#include <vector>
 
 struct dh_pipe {
     int device = 0;
@@ -27,6 +28,10 @@ struct dh_pipe {
     uint32_t* d_nsym = nullptr;
     float* d_stage = nullptr;     // device staging for host input
     size_t stage_pitch = 0;
+    // optional per-stage device timing (CUDA events on the caller's stream)
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;   // 4 per process call: start, after K1, after K2, after decoder
+    uint64_t launches = 0;             // kernels launched by this pipe since creation
 };
 
 extern "C" {
@@ -74,17 +79,64 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_device: handle is NULL");
     DH_REQUIRE(n <= h->max_chunk, DH_E_INVALID, "dh_pipe_process_device: n=%zu exceeds max_chunk=%zu", n, h->max_chunk);
     if (n == 0) return DH_OK;
-    int rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    auto mark = [&]() -> int {
+        if (!h->profiling) return DH_OK;
+        dh::DeviceGuard guard(h->device);
+        cudaEvent_t e;
+        DH_CUDA(cudaEventCreate(&e));
+        DH_CUDA(cudaEventRecord(e, st));
+        h->events.push_back(e);
+        return DH_OK;
+    };
+    int rc = mark();
+    if (rc != DH_OK) return rc;
     if (h->rrc) {
         rc = dh_rrc_process(h->rrc, d_in, in_pitch, h->d_filt, h->filt_pitch, n, stream);
         if (rc != DH_OK) return rc;
+        h->launches++;
+        if ((rc = mark()) != DH_OK) return rc;
         rc = dh_demod_process(h->demod, h->d_filt, h->filt_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, stream);
     } else {
+        if ((rc = mark()) != DH_OK) return rc;
         rc = dh_demod_process(h->demod, d_in, in_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, stream);
     }
     if (rc != DH_OK) return rc;
-    return dh_decoder_process(h->decoder, h->d_sym, h->sym_pitch, h->d_nsym, h->max_syms, stream);
+    h->launches++;
+    if ((rc = mark()) != DH_OK) return rc;
+    rc = dh_decoder_process(h->decoder, h->d_sym, h->sym_pitch, h->d_nsym, h->max_syms, stream);
+    if (rc != DH_OK) return rc;
+    h->launches++;
+    return mark();
 }
+
+int dh_pipe_set_profiling(dh_pipe* h, int enable) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_set_profiling: handle is NULL");
+    h->profiling = enable != 0;
+    return DH_OK;
+}
+
+int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_stage_times: handle is NULL");
+    dh::DeviceGuard guard(h->device);
+    double acc[3] = {0, 0, 0};
+    const size_t ncalls = h->events.size() / 4;
+    for (size_t c = 0; c < ncalls; c++) {
+        DH_CUDA(cudaEventSynchronize(h->events[4 * c + 3]));
+        for (int k = 0; k < 3; k++) {
+            float t = 0;
+            DH_CUDA(cudaEventElapsedTime(&t, h->events[4 * c + k], h->events[4 * c + k + 1]));
+            acc[k] += t;
+        }
+    }
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    h->events.clear();
+    if (ms) for (int k = 0; k < 3; k++) ms[k] = acc[k];
+    if (calls) *calls = ncalls;
+    return DH_OK;
+}
+
+uint64_t dh_pipe_launch_count(const dh_pipe* h) { return h ? h->launches : 0; }
 
 int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_host: handle is NULL");
@@ -141,6 +193,7 @@ size_t dh_pipe_host_pitch(const dh_pipe* h) { return h ? (h->max_chunk + 3) & ~(
 
 void dh_pipe_destroy(dh_pipe* h) {
     if (!h) return;
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     dh_rrc_destroy(h->rrc);
     dh_demod_destroy(h->demod);
     dh_decoder_destroy(h->decoder);

@@ -141,6 +141,11 @@ DH_API int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** da
 DH_API int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len);
 /* totals over all channels since creation */
 DH_API int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes);
+/* events replayed and bytes copied device->host by collect since creation */
+DH_API int dh_decoder_stats(dh_decoder* h, uint64_t* events, uint64_t* d2h_bytes);
+/* Drops the results pending ON THE DEVICE without copying them (asynchronous counter reset).  For callers that
+ * consume the device buffers themselves or only measure the kernels. */
+DH_API int dh_decoder_discard(dh_decoder* h, void* stream);
 /* drops the accumulated host results */
 DH_API int dh_decoder_clear(dh_decoder* h);
 DH_API void dh_decoder_destroy(dh_decoder* h);
@@ -169,6 +174,13 @@ DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
 DH_API dh_decoder* dh_pipe_decoder(dh_pipe* h);
 /* device views of the symbols the demodulator produced in the LAST process call (parity artefact) */
 DH_API int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, const uint32_t** d_nsym);
+/* Per-stage device timing: when enabled every process call records CUDA events on the caller's stream around
+ * K1 (RRC), K2 (demodulator) and the decoder kernel.  dh_pipe_stage_times waits for the recorded work, returns
+ * the summed milliseconds per stage since the previous query and the number of calls they cover. */
+DH_API int dh_pipe_set_profiling(dh_pipe* h, int enable);
+DH_API int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls);
+/* kernels launched by this pipe since creation */
+DH_API uint64_t dh_pipe_launch_count(const dh_pipe* h);
 /* synchronous host copy of one channel's symbols of the last process call (test / debug helper) */
 DH_API int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t cap, size_t* count);
 DH_API void dh_pipe_destroy(dh_pipe* h);
