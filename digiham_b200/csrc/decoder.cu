@@ -306,6 +306,22 @@ int dh_decoder_clear(dh_decoder* h) {
     return DH_OK;
 }
 
+int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, size_t cap, size_t* len) {
+    DH_REQUIRE(events != nullptr || n_events == 0, DH_E_INVALID, "dh_meta_replay: events is NULL");
+    dh::MetaReplay* r = nullptr;
+    switch (proto) {
+        case DH_PROTO_DMR: r = dh::make_dmr_replay(); break;
+        default: break;
+    }
+    DH_REQUIRE(r != nullptr, DH_E_UNSUPPORTED, "dh_meta_replay: protocol %d has no metadata replay", proto);
+    std::string text;
+    r->apply(static_cast<const DecEvent*>(events), n_events, text);
+    delete r;
+    if (len) *len = text.size();
+    if (out && cap) std::memcpy(out, text.data(), std::min(cap, text.size()));
+    return DH_OK;
+}
+
 void dh_decoder_destroy(dh_decoder* h) {
     if (!h) return;
     dh::DeviceGuard guard(h->device);

@@ -146,6 +146,11 @@ DH_API int dh_decoder_stats(dh_decoder* h, uint64_t* events, uint64_t* d2h_bytes
 /* Drops the results pending ON THE DEVICE without copying them (asynchronous counter reset).  For callers that
  * consume the device buffers themselves or only measure the kernels. */
 DH_API int dh_decoder_discard(dh_decoder* h, void* stream);
+/* Host-only helper (no GPU involved): replays n_events 16-byte decoder event records of ONE channel, in order,
+ * through a fresh metadata collector of the given protocol and returns the lines it would have written.
+ * Record layout: {u8 kind, u8 slot, u8 a, u8 b, u8 data[12]}; DMR kinds: 1 slot reset, 2 set sync a (+ soft reset
+ * if b), 3 soft reset, 4 link control (9 LC bytes in data), 5 talker-alias collector reset. */
+DH_API int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, size_t cap, size_t* len);
 /* drops the accumulated host results */
 DH_API int dh_decoder_clear(dh_decoder* h);
 DH_API void dh_decoder_destroy(dh_decoder* h);

@@ -1,0 +1,125 @@
+"""CPU suite, part 1: the oracle(s) against the committed golden fixtures (tests/golden/golden_v1.npz, generated from
+the compiled reference by tests/golden/make_golden.py), and the two oracles against each other where both exist.
+Nothing here needs a GPU."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib
+
+GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+
+
+def _oracles():
+    out = []
+    if oracle_lib.ref() is not None:
+        out.append(oracle_lib.ref())
+    if os.listdir(os.path.join(oracle_lib.ORACLE_DIR, "port")):
+        out.append(oracle_lib.port())
+    return out
+
+
+ORACLES = _oracles()
+IDS = [o.kind for o in ORACLES]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def test_an_oracle_exists():
+    assert ORACLES, "neither oracle/_ref/libdigiham_ref.so nor oracle/port is available"
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_rrc_golden(orc):
+    x = GOLDEN["rrc_in"]
+    assert np.array_equal(_bits(orc.rrc(x, narrow=False)), _bits(GOLDEN["rrc_wide_out"]))
+    assert np.array_equal(_bits(orc.rrc(x, narrow=True)), _bits(GOLDEN["rrc_narrow_out"]))
+    # chunked feeding changes nothing (src/lib/cli.cpp:29-33 drain loop)
+    assert np.array_equal(_bits(orc.rrc(x, narrow=False, chunk=37)), _bits(GOLDEN["rrc_wide_out"]))
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_demod_golden(orc):
+    assert np.array_equal(orc.demod(GOLDEN["gfsk10_in"], sps=10, four_level=True), GOLDEN["gfsk10_out"])
+    assert np.array_equal(orc.demod(GOLDEN["gfsk10_in"], sps=10, four_level=True, chunk=128), GOLDEN["gfsk10_out"])
+    assert np.array_equal(orc.demod(GOLDEN["fsk40_in"], sps=40, four_level=False, invert=True),
+                          GOLDEN["fsk40_inv_out"])
+    assert np.array_equal(orc.demod(GOLDEN["fsk40_in"], sps=40, four_level=False, invert=False), GOLDEN["fsk40_out"])
+    # the inverted output is the complement
+    assert np.array_equal(GOLDEN["fsk40_inv_out"] ^ 1, GOLDEN["fsk40_out"])
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_dmr_decoder_golden(orc):
+    for k in range(2):
+        out, meta = orc.decode(oracle_lib.PROTO_DMR, GOLDEN["dmr%d_sym" % k])
+        assert np.array_equal(out, GOLDEN["dmr%d_out" % k])
+        assert meta == GOLDEN["dmr%d_meta" % k].tobytes()
+        out2, meta2 = orc.decode(oracle_lib.PROTO_DMR, GOLDEN["dmr%d_sym" % k], chunk=100)
+        assert np.array_equal(out2, out) and meta2 == meta
+    assert b"sync:voice" in GOLDEN["dmr0_meta"].tobytes() and b"talkeralias:B200 TESTER" in GOLDEN["dmr0_meta"].tobytes()
+    assert GOLDEN["dmr0_out"].size % 27 == 0 and GOLDEN["dmr0_out"].size > 0
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_pipe_golden(orc):
+    for c in range(2):
+        sym, out, meta = orc.pipe(oracle_lib.PROTO_DMR, GOLDEN["pipe%d_in" % c], chunk=1000)
+        assert np.array_equal(sym, GOLDEN["pipe%d_sym" % c])
+        assert np.array_equal(out, GOLDEN["pipe%d_out" % c])
+        assert meta == GOLDEN["pipe%d_meta" % c].tobytes()
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_block_codes_golden(orc):
+    for cid, name in enumerate(oracle_lib.FEC_NAMES):
+        table = GOLDEN["fec_" + name]
+        for s in range(table.shape[0]):
+            ok, w = orc.fec(cid, s)
+            assert (int(ok), w) == (int(table[s, 0]), int(table[s, 1])), (name, s)
+    for p, exp in zip(GOLDEN["bptc_in"], GOLDEN["bptc_out"]):
+        ok, out = orc.bptc(p)
+        assert int(ok) == exp[0]
+        if ok:
+            assert np.array_equal(out, exp[1:])
+    assert GOLDEN["bptc_out"][:10, 0].all(), "valid BPTC blocks with <= 4 bit errors must decode"
+
+
+def test_generated_luts_match_reference_for_every_syndrome():
+    """tools/gen_tables.py derives H and the correction LUTs from the published generator matrices; the result
+    must equal what the reference's linear search over corrections[] does (golden = compiled reference)."""
+    import re
+    src = open(os.path.join(oracle_lib.ROOT, "digiham_b200", "csrc", "tables.inc")).read()
+
+    def macro(name):
+        m = re.search(r"#define %s \{ \\\n(.*?)\n\}" % name, src, re.S)
+        return [int(v.strip().rstrip("u"), 16) for v in m.group(1).replace("\\", " ").replace("\n", " ").split(",")
+                if v.strip()]
+
+    for name in oracle_lib.FEC_NAMES:
+        lut = macro("DH_%s_LUT_INIT" % name.upper())
+        table = GOLDEN["fec_" + name]
+        assert len(lut) == table.shape[0]
+        for s in range(len(lut)):
+            ok = s == 0 or lut[s] != 0
+            assert ok == bool(table[s, 0]), (name, s)
+            if ok:
+                assert (s ^ lut[s]) == int(table[s, 1]), (name, s)
+
+
+@pytest.mark.skipif(len(ORACLES) < 2, reason="needs both the compiled reference and the port")
+def test_port_equals_reference_on_random_streams():
+    ref, port = oracle_lib.ref(), oracle_lib.port()
+    from digiham_b200 import synth
+    rng = np.random.default_rng(5)
+    x = rng.normal(0, 0.3, 5000).astype(np.float32)
+    for narrow in (False, True):
+        assert np.array_equal(_bits(ref.rrc(x, narrow)), _bits(port.rrc(x, narrow)))
+    xb, _ = synth.dmr_channel_bank(6, 40000, seed=9, device="cpu")
+    for c in range(6):
+        a = ref.pipe(oracle_lib.PROTO_DMR, xb[c, :40000].numpy())
+        b = port.pipe(oracle_lib.PROTO_DMR, xb[c, :40000].numpy())
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
