@@ -16,6 +16,7 @@ from ._capi import (  # noqa: F401
     DemodBank,
     DecoderBank,
     Pipe,
+    DvfBank,
     PROTO_DMR,
     PROTO_YSF,
     PROTO_POCSAG,
@@ -23,4 +24,4 @@ from ._capi import (  # noqa: F401
     RRC_NARROW,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]

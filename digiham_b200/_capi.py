@@ -92,6 +92,12 @@ def lib():
     L.dh_decoder_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
     L.dh_pipe_destroy.restype = None
+    L.dh_dvf_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32]
+    L.dh_dvf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
+                                 ctypes.c_size_t, ctypes.c_void_p]
+    L.dh_dvf_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_dvf_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_dvf_destroy.restype = None
     _lib = L
     return L
 
@@ -362,6 +368,39 @@ class Pipe:
     def close(self):
         if self._h:
             lib().dh_pipe_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DvfBank:
+    """N x Digiham::DigitalVoice::DigitalVoiceFilter (reference include/digitalvoice_filter.hpp:12-19)."""
+
+    def __init__(self, channels, device="cuda:0"):
+        self._h = ctypes.c_void_p()
+        self.channels = int(channels)
+        check(lib().dh_dvf_create(ctypes.byref(self._h), _dev_index(device), self.channels))
+
+    def process(self, x, out=None, n=None, stream=None):
+        assert x.is_cuda and x.dtype == torch.int16 and x.dim() == 2 and x.shape[0] == self.channels
+        if n is None:
+            n = x.shape[1]
+        if out is None:
+            out = torch.empty_like(x)
+        check(lib().dh_dvf_process(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n,
+                                   _stream_ptr(stream)))
+        return out
+
+    def reset(self, stream=None):
+        check(lib().dh_dvf_reset(self._h, _stream_ptr(stream)))
+
+    def close(self):
+        if self._h:
+            lib().dh_dvf_destroy(self._h)
             self._h = ctypes.c_void_p()
 
     def __del__(self):

@@ -157,6 +157,7 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
     const dh::ProtoOps* ops = nullptr;
     switch (proto) {
         case DH_PROTO_DMR: ops = dh::dmr_ops(); break;
+        case DH_PROTO_POCSAG: ops = dh::pocsag_ops(); break;
         default: break;
     }
     DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "dh_decoder_create: protocol %d not supported", proto);

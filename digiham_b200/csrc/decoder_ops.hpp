@@ -19,5 +19,6 @@ struct ProtoOps {
 };
 
 const ProtoOps* dmr_ops();
+const ProtoOps* pocsag_ops();
 
 }  // namespace dh

@@ -354,3 +354,72 @@ def dmr_channel_bank(channels, n_samples, seed=0, device="cpu", pool=48, noise_f
                        seed=seed + 1, device=device)
     info = {"noise_only": noise_only, "snr_db": snr, "ppm": ppm}
     return x, info
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# POCSAG (reference src/pocsag_decoder/*): preamble, then batches of
+# FSC 0x7CD215D8 + 16 codewords; codeword = flag(1) payload(20) BCH(10) even-parity(1), MSB first.
+POCSAG_FSC = 0x7CD215D8
+POCSAG_IDLE = 0x7A89C197
+
+
+def pocsag_codeword(flag, payload20):
+    data21 = ((flag & 1) << 20) | (payload20 & 0xFFFFF)
+    cw31 = bch_31_21_encode(data21)
+    cw = cw31 << 1
+    return cw | (bin(cw).count("1") & 1)
+
+
+def pocsag_alpha_payloads(text):
+    bits = []
+    for ch in text.encode("ascii"):
+        bits += [(ch >> j) & 1 for j in range(7)]          # LSB first per character
+    while len(bits) % 20:
+        bits.append(0)
+    return [int("".join(str(b) for b in bits[i:i + 20]), 2) for i in range(0, len(bits), 20)]
+
+
+def pocsag_bits(messages, seed=0, preamble=576, bit_errors=0, trailing_batches=1, lead_in=0):
+    """messages: list of (address, function, text).  Returns the bit stream (uint8 0/1) the demodulator should
+    emit.  bit_errors random bit flips are injected into every codeword (<= 2 are correctable)."""
+    rng = np.random.default_rng(seed)
+    words = []          # list of batches, each 16 codewords
+
+    def new_batch():
+        words.append([POCSAG_IDLE] * 16)
+
+    new_batch()
+    slot = 0
+    for address, function, text in messages:
+        frame = address & 7
+        start = frame * 2
+        if slot > start:
+            new_batch()
+            slot = 0
+        slot = start
+        queue = [pocsag_codeword(0, ((address >> 3) << 2) | (function & 3))]
+        queue += [pocsag_codeword(1, p) for p in pocsag_alpha_payloads(text)]
+        for cw in queue:
+            if slot >= 16:
+                new_batch()
+                slot = 0
+            words[-1][slot] = cw
+            slot += 1
+        if slot >= 16:
+            new_batch()
+            slot = 0
+        else:
+            slot += 1       # at least one idle codeword terminates the message
+    for _ in range(trailing_batches):
+        new_batch()
+    out = [rng.integers(0, 2, size=lead_in).astype(np.uint8)] if lead_in else []
+    out.append((np.arange(preamble) % 2 == 0).astype(np.uint8))
+    for batch in words:
+        out.append(_int_to_bits(POCSAG_FSC, 32))
+        for cw in batch:
+            b = _int_to_bits(cw, 32)
+            if bit_errors:
+                for e in rng.choice(32, size=bit_errors, replace=False):
+                    b[e] ^= 1
+            out.append(b)
+    return np.concatenate(out).astype(np.uint8)

@@ -22,6 +22,8 @@
  *   dh_demod_*    Digiham::Fsk::GfskDemodulator(sps)                               include/gfsk_demodulator.hpp:12-33
  *                 Digiham::Fsk::FskDemodulator(sps, invert)                        include/fsk_demodulator.hpp:12-33
  *                 canProcess()/process()              src/gfsk_demodulator/gfsk_demodulator.cpp:18-122, src/fsk_demodulator/fsk_demodulator.cpp:19-112
+ *   dh_dvf_*      Digiham::DigitalVoice::DigitalVoiceFilter::process              include/digitalvoice_filter.hpp:12-19,
+ *                                                                 src/digitalvoice_filter/digitalvoice_filter.cpp:6-45
  *   dh_decoder_*  Digiham::Decoder::{canProcess,process,setMetaWriter}             include/decoder.hpp:17-30, src/lib/decoder.cpp:21-47
  *                 Digiham::Dmr::Decoder::{Decoder,setSlotFilter}                   include/dmr_decoder.hpp:9-17, src/dmr_decoder/dmr_phase.cpp:35-345
  */
@@ -106,6 +108,19 @@ DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, siz
                             size_t sym_pitch, uint32_t* d_nsym, void* stream);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * DigitalVoiceFilter bank — N x Digiham::DigitalVoice::DigitalVoiceFilter: 10th-order Butterworth band-pass on
+ * 8 kHz int16 audio (src/digitalvoice_filter/digitalvoice_filter.cpp:34-45), mixed float/double recurrence and the
+ * x86 (short) truncation reproduced exactly.  In-place operation (d_out == d_in) is allowed.
+ */
+typedef struct dh_dvf dh_dvf;
+
+DH_API int dh_dvf_create(dh_dvf** out, int device, uint32_t channels);
+DH_API int dh_dvf_process(dh_dvf* h, const int16_t* d_in, size_t in_pitch, int16_t* d_out, size_t out_pitch,
+                          size_t n, void* stream);
+DH_API int dh_dvf_reset(dh_dvf* h, void* stream);
+DH_API void dh_dvf_destroy(dh_dvf* h);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Protocol decoder bank — N x Digiham::Dmr::Decoder / Ysf::Decoder / Pocsag::Decoder.
