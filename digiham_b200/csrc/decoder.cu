@@ -158,6 +158,7 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
     switch (proto) {
         case DH_PROTO_DMR: ops = dh::dmr_ops(); break;
         case DH_PROTO_POCSAG: ops = dh::pocsag_ops(); break;
+        case DH_PROTO_YSF: ops = dh::ysf_ops(); break;
         default: break;
     }
     DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "dh_decoder_create: protocol %d not supported", proto);
@@ -312,6 +313,7 @@ int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, 
     dh::MetaReplay* r = nullptr;
     switch (proto) {
         case DH_PROTO_DMR: r = dh::make_dmr_replay(); break;
+        case DH_PROTO_YSF: r = dh::make_ysf_replay(); break;
         default: break;
     }
     DH_REQUIRE(r != nullptr, DH_E_UNSUPPORTED, "dh_meta_replay: protocol %d has no metadata replay", proto);

@@ -20,5 +20,6 @@ struct ProtoOps {
 
 const ProtoOps* dmr_ops();
 const ProtoOps* pocsag_ops();
+const ProtoOps* ysf_ops();
 
 }  // namespace dh

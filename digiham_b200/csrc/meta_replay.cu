@@ -253,8 +253,174 @@ class DmrReplay: public MetaReplay {
         }
 };
 
+// ---- YSF ---------------------------------------------------------------------------------------------------------
+// Restates Ysf::MetaCollector (src/ysf_decoder/ysf_meta.cpp:7-105) incl. the hold/release batching of the base
+// class (src/lib/meta.cpp:71-100), FramePhase::treatYsfString (ysf_phase.cpp:351-361), DataCollector / DataFrame
+// (data.cpp:15-88) and Ysf::Gps::parse (gps.cpp:7-105).
+
+class YsfReplay: public MetaReplay {
+    public:
+        void apply(const DecEvent* ev, uint32_t n, std::string& out) override {
+            for (uint32_t i = 0; i < n; i++) {
+                const DecEvent& e = ev[i];
+                switch (e.kind) {
+                    case 1: {
+                        static const char* const names[] = {"", "V1", "DN", "VW", "FR data"};
+                        set(mode, names[e.a <= 4 ? e.a : 0], out);
+                        break;
+                    }
+                    case 2: reset(out); break;
+                    case 3: held++; break;
+                    case 4: {
+                        const std::string v = treat(e.data);
+                        switch (e.a) {
+                            case 0: set(destination, v, out); break;
+                            case 1: set(source, v, out); break;
+                            case 2: set(down, v, out); break;
+                            case 3: set(up, v, out); break;
+                        }
+                        break;
+                    }
+                    case 5: release(out); break;
+                    case 6: dcNext = 0; break;
+                    case 7:
+                        if (e.a != dcNext) {
+                            dcNext = 0;
+                        } else {
+                            dcNext = e.a + 1;
+                            std::memcpy(dcData + (e.a & 1) * 10, e.data, 10);
+                        }
+                        break;
+                    case 8:
+                        if (dcNext >= 2) checkDataFrame(out);
+                        break;
+                }
+            }
+        }
+    private:
+        std::string mode, destination, source, up, down;
+        bool hasCoord = false;
+        float lat = 0, lon = 0;
+        int held = 0;
+        bool dirty = false;
+        unsigned dcNext = 0;
+        unsigned char dcData[20] = {0};
+
+        void send(std::string& out) {
+            if (held) {
+                dirty = true;
+                return;
+            }
+            std::map<std::string, std::string> kv;
+            kv["protocol"] = "YSF";
+            if (!mode.empty()) kv["mode"] = mode;
+            if (!destination.empty()) kv["target"] = destination;
+            if (!source.empty()) kv["source"] = source;
+            if (!up.empty()) kv["up"] = up;
+            if (!down.empty()) kv["down"] = down;
+            if (hasCoord) {
+                kv["lat"] = std::to_string(lat);
+                kv["lon"] = std::to_string(lon);
+            }
+            out += serialize(kv);
+        }
+        void set(std::string& field, const std::string& v, std::string& out) {
+            if (field == v) return;
+            field = v;
+            send(out);
+        }
+        void setGps(bool valid, float la, float lo, std::string& out) {
+            if (!valid && !hasCoord) return;
+            if (valid && hasCoord && lat == la && lon == lo) return;
+            hasCoord = valid;
+            lat = la;
+            lon = lo;
+            send(out);
+        }
+        void release(std::string& out) {
+            held--;
+            if (held == 0) {
+                if (dirty) send(out);
+                dirty = false;
+            }
+        }
+        void reset(std::string& out) {
+            held++;
+            set(mode, "", out);
+            set(destination, "", out);
+            set(source, "", out);
+            set(up, "", out);
+            set(down, "", out);
+            setGps(false, 0, 0, out);
+            release(out);
+        }
+        static std::string treat(const uint8_t* input) {
+            size_t length = 10;
+            for (char ch : {'\n', ' '}) {
+                const void* end = std::memchr(input, ch, length);
+                if (end != nullptr) length = (size_t) ((const uint8_t*) end - input);
+            }
+            return latin1_to_utf8(input, length);
+        }
+        void checkDataFrame(std::string& out) {
+            if (dcData[18] != 0x03) return;
+            uint8_t checksum = 0;
+            for (int i = 0; i < 19; i++) checksum = (uint8_t) (checksum + dcData[i]);
+            if (checksum != dcData[19]) return;
+            const uint32_t command = (uint32_t) dcData[1] << 16 | (uint32_t) dcData[2] << 8 | dcData[3];
+            float la = 0, lo = 0;
+            bool valid = command == 0x22625f && parseGps(dcData + 5, la, lo);   // COMMAND_SHORT_GPS
+            setGps(valid, la, lo, out);
+        }
+        static bool parseGps(const uint8_t* d, float& latOut, float& lonOut) {
+            for (int i = 0; i < 6; i++) {
+                if ((d[i] & 0x0F) > 9) return false;
+            }
+            float la = (float) ((d[0] & 0x0F) * 10 + (d[1] & 0x0F));
+            la = la + (float) (d[2] & 0x0F) / 6;
+            la = la + (float) (d[3] & 0x0F) / 60;
+            la = la + (float) (d[4] & 0x0F) / 600;
+            la = la + (float) (d[5] & 0x0F) / 6000;
+            uint8_t direction = d[3] & 0xF0;
+            if (direction == 0x50) {
+            } else if (direction == 0x30) {
+                la *= -1;
+            } else {
+                return false;
+            }
+            float lo = 0;   // the reference leaves lon uninitialised when neither branch matches (gps.cpp:37-55)
+            uint8_t b = d[4] & 0xF0;
+            const uint8_t c = d[6];
+            if (b == 0x50) {
+                if (c >= 0x76 && c < 0x7f) lo = (float) (c - 0x76);
+                else if (c >= 0x6c && c < 0x75) lo = (float) (100 + (c - 0x6c));
+                else if (c >= 0x26 && c < 0x6b) lo = (float) (110 + (c - 0x26));
+                else return false;
+            } else if (b == 0x30) {
+                if (c >= 0x26 && c < 0x7f) lo = (float) (10 + (c - 0x26));
+                else return false;
+            }
+            b = d[7];
+            if (b > 0x58 && b <= 0x61) lo += (float) (b - 0x58) / 60;
+            else if (b >= 0x26 && b <= 0x57) lo += (float) (10 + (b - 0x26)) / 60;
+            else return false;
+            b = d[8];
+            if (b >= 0x1c && b < 0x7f) lo += (float) (b - 0x1c) / 6000;
+            else return false;
+            direction = d[5] & 0xF0;
+            if (direction == 0x50) lo *= -1;
+            else if (direction != 0x30) return false;
+            if (la > 90 || la < -90) return false;
+            if (lo > 180 || lo < -180) return false;
+            latOut = la;
+            lonOut = lo;
+            return true;
+        }
+};
+
 }  // namespace
 
 MetaReplay* make_dmr_replay() { return new DmrReplay(); }
+MetaReplay* make_ysf_replay() { return new YsfReplay(); }
 
 }  // namespace dh

@@ -14,5 +14,6 @@ class MetaReplay {
 };
 
 MetaReplay* make_dmr_replay();
+MetaReplay* make_ysf_replay();
 
 }  // namespace dh

@@ -423,3 +423,168 @@ def pocsag_bits(messages, seed=0, preamble=576, bit_errors=0, trailing_batches=1
                     b[e] ^= 1
             out.append(b)
     return np.concatenate(out).astype(np.uint8)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# YSF (reference src/ysf_decoder/*): 480-dibit frames = sync(20) FICH(100) payload(360)
+YSF_SYNC = _hex_to_dibits("D471C9634D")
+
+
+def crc16_ccitt(data):
+    """crc16_checksum of the reference (src/ysf_decoder/crc16.c:3-19): poly 0x1021, init 0, final inversion."""
+    crc = 0
+    for byte in data:
+        for i in range(8):
+            inp = (int(byte) >> (7 - i)) & 1
+            nx = inp ^ ((crc >> 15) & 1)
+            crc = (crc << 1) & 0xFFFF
+            crc ^= (nx << 12) | (nx << 5) | nx
+    return crc ^ 0xFFFF
+
+
+def pn9_bits(n):
+    """Whitening sequence of src/ysf_decoder/whitening.c:7-20."""
+    wsr = 0b111001001
+    out = np.zeros(n, dtype=np.uint8)
+    for i in range(n):
+        wb = wsr & 1
+        out[i] = wb
+        fb = ((wsr >> 4) & 1) ^ wb
+        wsr = ((wsr & 0b111111110) >> 1) | (fb << 8)
+    return out
+
+
+def ysf_conv_encode(bits):
+    """Rate-1/2 K=5 encoder matching trellis_transitions (src/ysf_decoder/trellis.c:8-25): state = last four
+    input bits, newest at the MSB; returns one dibit per input bit."""
+    state = 0
+    out = np.zeros(len(bits), dtype=np.uint8)
+    for i, b in enumerate(bits):
+        t = 3 if b else 0
+        if state & 1:
+            t ^= 3
+        if state & 2:
+            t ^= 2
+        if state & 4:
+            t ^= 1
+        if state & 8:
+            t ^= 1
+        out[i] = t
+        state = (int(b) << 3) | (state >> 1)
+    return out
+
+
+def ysf_fich_dibits(fi, fn, dt, rng):
+    """FICH: FI at bits 31-30, FN at 21-19, DT at 9-8 (src/ysf_decoder/fich.cpp:56-66); other bits random."""
+    fich = int(rng.integers(0, 1 << 32))
+    fich &= ~((3 << 30) | (7 << 19) | (3 << 8))
+    fich |= (fi << 30) | (fn << 19) | (dt << 8)
+    be = [(fich >> 24) & 0xFF, (fich >> 16) & 0xFF, (fich >> 8) & 0xFF, fich & 0xFF]
+    crc = crc16_ccitt(be)
+    bits48 = _int_to_bits((fich << 16) | crc, 48)
+    coded = []
+    for i in range(4):
+        data12 = int("".join(str(b) for b in bits48[12 * i:12 * i + 12]), 2)
+        coded.append(_int_to_bits(encode_block("golay_24_12", data12), 24))
+    bits = np.concatenate(coded + [np.zeros(4, dtype=np.uint8)])
+    enc = ysf_conv_encode(bits)
+    tx = np.zeros(100, dtype=np.uint8)
+    for i in range(100):
+        tx[(i * 20) % 100 + (i * 20) // 100] = enc[i]
+    return tx
+
+
+def _ysf_dch_encode(data, rng):
+    """data: 10 or 20 bytes -> conv-encoded dibits (100 or 180): whiten, CRC16 over the whitened bytes, 4 tail bits."""
+    data = np.asarray(data, dtype=np.uint8)
+    nbits = data.size * 8
+    w = np.packbits(np.unpackbits(data) ^ pn9_bits(nbits))
+    crc = crc16_ccitt(w)
+    bits = np.concatenate([np.unpackbits(w), _int_to_bits(crc, 16), np.zeros(4, dtype=np.uint8)])
+    return ysf_conv_encode(bits)
+
+
+def _callsign(text):
+    b = text.encode("latin-1")[:10]
+    return np.frombuffer(b + b" " * (10 - len(b)), dtype=np.uint8)
+
+
+def ysf_gps_frames(lat_digits=(4, 8, 0, 7, 3, 0), south=False, west=False, lon_c=0x30, lon_min=0x40, lon_frac=0x30,
+                   radio=0x28, lon_hi=0x30):
+    """DT1 + DT2 (2 x 10 bytes) of a short-GPS data frame (src/ysf_decoder/data.cpp:34-88, gps.cpp:7-105)."""
+    d = np.zeros(20, dtype=np.uint8)
+    d[1:4] = [0x22, 0x62, 0x5F]
+    d[4] = radio
+    g = [0x30 | v for v in lat_digits]
+    g[3] = (0x30 if south else 0x50) | lat_digits[3]
+    g[4] = lon_hi | lat_digits[4]
+    g[5] = (0x50 if west else 0x30) | lat_digits[5]
+    d[5:11] = g
+    d[11] = lon_c
+    d[12] = lon_min
+    d[13] = lon_frac
+    d[18] = 0x03
+    d[19] = int(d[:19].sum()) & 0xFF
+    return d[:10], d[10:]
+
+
+def ysf_frame(fi, fn, dt, rng, fields=None, gps=None):
+    """One 480-dibit frame.  fields: dict with 'dest','src','down','up' callsigns."""
+    fields = fields or {}
+    f = np.zeros(480, dtype=np.uint8)
+    f[0:20] = YSF_SYNC
+    f[20:120] = ysf_fich_dibits(fi, fn, dt, rng)
+    payload = rng.integers(0, 4, size=360).astype(np.uint8)
+    if fi in (0, 2):
+        for which, (a, b) in enumerate([("dest", "src"), ("down", "up")]):
+            csd = np.concatenate([_callsign(fields.get(a, "")), _callsign(fields.get(b, ""))])
+            enc = _ysf_dch_encode(csd, rng)
+            for i in range(180):
+                streampos = (i % 9) * 20 + i // 9
+                payload[(streampos // 36) * 72 + streampos % 36 + 36 * which] = enc[i]
+    elif dt == 2:
+        if fn <= 3:
+            data = _callsign(fields.get(["dest", "src", "down", "up"][fn], ""))
+        elif fn >= 6 and gps is not None:
+            data = gps[fn - 6]
+        else:
+            data = rng.integers(0, 256, size=10).astype(np.uint8)
+        enc = _ysf_dch_encode(data, rng)
+        for i in range(100):
+            payload[(i % 5) * 72 + i // 5] = enc[i]
+    f[120:480] = payload
+    return f
+
+
+def ysf_symbols(n_frames, seed=0, mode="DN", lead_in=None, symbol_errors=0.0):
+    """A YSF transmission: header, n communication frames of the given mode ('DN' = V/D2, 'V1', 'VW' = voice FR,
+    'FR' = data FR, 'mix'), terminator, then noise; repeated until n_frames frames exist."""
+    rng = np.random.default_rng(seed)
+    calls = ["DL1ABC", "ALL", "RPT-DOWN", "RPT-UP", "JA1YSF", "W1AW", "B200 TEST", "X"]
+    if lead_in is None:
+        lead_in = int(rng.integers(0, 300))
+    out = [rng.integers(0, 4, size=lead_in).astype(np.uint8)]
+    made = 0
+    while made < n_frames:
+        fields = {"dest": calls[int(rng.integers(0, 8))], "src": calls[int(rng.integers(0, 8))],
+                  "down": calls[int(rng.integers(0, 8))], "up": calls[int(rng.integers(0, 8))]}
+        gps = ysf_gps_frames(lat_digits=tuple(int(v) for v in rng.integers(0, 6, size=6)),
+                             south=bool(rng.integers(0, 2)), west=bool(rng.integers(0, 2)),
+                             lon_c=int(rng.integers(0x26, 0x7f)), lon_min=int(rng.integers(0x26, 0x58)),
+                             lon_frac=int(rng.integers(0x1c, 0x7f)))
+        m = mode if mode != "mix" else ["DN", "V1", "VW", "FR"][int(rng.integers(0, 4))]
+        dt = {"V1": 0, "FR": 1, "DN": 2, "VW": 3}[m]
+        out.append(ysf_frame(0, 0, dt, rng, fields))
+        made += 1
+        n_comm = int(rng.integers(6, 20))
+        for k in range(n_comm):
+            out.append(ysf_frame(1, k % 8, dt, rng, fields, gps))
+            made += 1
+        out.append(ysf_frame(2, 0, dt, rng, fields))
+        made += 1
+        out.append(rng.integers(0, 4, size=int(rng.integers(0, 700))).astype(np.uint8))
+    s = np.concatenate(out)
+    if symbol_errors > 0:
+        hit = rng.random(s.size) < symbol_errors
+        s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
+    return s
