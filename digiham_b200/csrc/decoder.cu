@@ -136,6 +136,7 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
         h->total_events += ev_len[c];
         if (ev_len[c] && h->replay[c]) {
             const size_t before = r.meta.size();
+            h->replay[c]->kv_sink = &r.meta_kv;
             h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
             h->total_meta += r.meta.size() - before;
         }
@@ -277,6 +278,13 @@ int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* 
     return DH_OK;
 }
 
+int dh_decoder_meta_kv(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len) {
+    DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_meta_kv: bad handle or channel");
+    if (data) *data = reinterpret_cast<const uint8_t*>(h->results[channel].meta_kv.data());
+    if (len) *len = h->results[channel].meta_kv.size();
+    return DH_OK;
+}
+
 int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_totals: handle is NULL");
     if (out_bytes) *out_bytes = h->total_bytes;
@@ -304,6 +312,7 @@ int dh_decoder_clear(dh_decoder* h) {
     for (auto& r : h->results) {
         r.bytes.clear();
         r.meta.clear();
+        r.meta_kv.clear();
     }
     return DH_OK;
 }

@@ -93,6 +93,7 @@ __device__ __forceinline__ uint32_t parity32(uint32_t v) { return __popc(v) & 1u
 struct ChannelResult {
     std::string bytes;
     std::string meta;
+    std::string meta_kv;   // same updates as key/value records (see MetaReplay::kv_sink)
 };
 
 }  // namespace dh

@@ -14,6 +14,27 @@
 namespace dh {
 
 namespace {
+std::string serialize(const std::map<std::string, std::string>& kv);
+}
+
+void MetaReplay::emit(const std::map<std::string, std::string>& kv, std::string& out) {
+    out += serialize(kv);
+    if (kv_sink) {
+        auto put16 = [&](size_t v) {
+            kv_sink->push_back((char) (v & 0xFF));
+            kv_sink->push_back((char) ((v >> 8) & 0xFF));
+        };
+        put16(kv.size());
+        for (const auto& it : kv) {
+            put16(it.first.size());
+            kv_sink->append(it.first);
+            put16(it.second.size());
+            kv_sink->append(it.second);
+        }
+    }
+}
+
+namespace {
 
 std::string serialize(const std::map<std::string, std::string>& kv) {
     std::string out;
@@ -248,7 +269,7 @@ class DmrReplay: public MetaReplay {
                 kv["lat"] = std::to_string(sl.lat);
                 kv["lon"] = std::to_string(sl.lon);
             }
-            out += serialize(kv);
+            emit(kv, out);
             sl.dirty = false;
         }
 };
@@ -322,7 +343,7 @@ class YsfReplay: public MetaReplay {
                 kv["lat"] = std::to_string(lat);
                 kv["lon"] = std::to_string(lon);
             }
-            out += serialize(kv);
+            emit(kv, out);
         }
         void set(std::string& field, const std::string& v, std::string& out) {
             if (field == v) return;

@@ -2,6 +2,7 @@
 #pragma once
 #include "decoder.cuh"
 
+#include <map>
 #include <string>
 
 namespace dh {
@@ -11,6 +12,11 @@ class MetaReplay {
         virtual ~MetaReplay() = default;
         // consumes n events of ONE channel in order and appends the resulting lines to out
         virtual void apply(const DecEvent* ev, uint32_t n, std::string& out) = 0;
+        // optional second sink: the same updates as length-prefixed key/value records (for callers that run their
+        // own Digiham::Serializer): per update u16 pairs, then per pair u16 klen, key, u16 vlen, value (little endian)
+        std::string* kv_sink = nullptr;
+    protected:
+        void emit(const std::map<std::string, std::string>& kv, std::string& out);
 };
 
 MetaReplay* make_dmr_replay();

@@ -55,6 +55,8 @@ DH_API const char* dh_last_error(void);
 DH_API const char* dh_version(void);
 /* number of CUDA devices visible to the library; DH_E_NODEVICE if there is none */
 DH_API int dh_device_count(int* count);
+/* frees the device staging the *_process_host variants cached for a bank handle (call before destroying it) */
+DH_API void dh_host_scratch_release(const void* handle);
 
 /* ------------------------------------------------------------------------------------------------------------
  * RRC FIR bank — N x Digiham::RrcFilter::RrcFilter (include/rrc_filter.hpp:10-31).
@@ -80,6 +82,9 @@ DH_API int dh_rrc_create_custom(dh_rrc** out, int device, uint32_t channels, uin
 DH_API int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
                    void* stream);
 /* back to power-on state (zero history) */
+/* Host-buffer variant (synchronous): h_in/h_out are [channels][pitch] in host memory; staging is internal. */
+DH_API int dh_rrc_process_host(dh_rrc* h, uint32_t channels, const float* h_in, size_t in_pitch, float* h_out,
+                               size_t out_pitch, size_t n);
 DH_API int dh_rrc_reset(dh_rrc* h, void* stream);
 DH_API void dh_rrc_destroy(dh_rrc* h);
 
@@ -106,6 +111,9 @@ DH_API size_t dh_demod_max_symbols(const dh_demod* h, size_t n);
  * count for this call to d_nsym[c].  sym_pitch >= dh_demod_max_symbols(h, n). */
 DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, uint8_t* d_sym,
                             size_t sym_pitch, uint32_t* d_nsym, void* stream);
+/* Host-buffer variant (synchronous); h_nsym receives the per-channel symbol counts of this call. */
+DH_API int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_in, size_t in_pitch, size_t n,
+                                 uint8_t* h_sym, size_t sym_pitch, uint32_t* h_nsym);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);
 
@@ -119,6 +127,8 @@ typedef struct dh_dvf dh_dvf;
 DH_API int dh_dvf_create(dh_dvf** out, int device, uint32_t channels);
 DH_API int dh_dvf_process(dh_dvf* h, const int16_t* d_in, size_t in_pitch, int16_t* d_out, size_t out_pitch,
                           size_t n, void* stream);
+DH_API int dh_dvf_process_host(dh_dvf* h, uint32_t channels, const int16_t* h_in, size_t in_pitch, int16_t* h_out,
+                               size_t out_pitch, size_t n);
 DH_API int dh_dvf_reset(dh_dvf* h, void* stream);
 DH_API void dh_dvf_destroy(dh_dvf* h);
 
@@ -148,12 +158,19 @@ DH_API int dh_decoder_set_slot_filter(dh_decoder* h, int channel, uint8_t filter
 /* Consumes d_nsym[c] (<= max_nsym) new symbols of every channel c (d_nsym is a DEVICE array). */
 DH_API int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, const uint32_t* d_nsym,
                               size_t max_nsym, void* stream);
+/* Host-buffer variant (synchronous): consumes h_nsym[c] symbols of every channel from host rows and collects. */
+DH_API int dh_decoder_process_host(dh_decoder* h, uint32_t channels, const uint8_t* h_sym, size_t sym_pitch,
+                                   const uint32_t* h_nsym);
 /* Synchronises with `stream`, copies everything produced since the last collect to the host and appends it to
  * the per-channel host buffers.  Must be called at least once every 2 process calls. */
 DH_API int dh_decoder_collect(dh_decoder* h, void* stream);
 /* Host views of one channel's accumulated results; valid until the next collect / clear / destroy. */
 DH_API int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len);
 DH_API int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len);
+/* The same metadata updates as key/value records, for callers that apply their own Digiham::Serializer
+ * (include/meta.hpp:10-19): per update u16 pair count, then per pair u16 key length, key, u16 value length, value
+ * (little endian, keys in std::map order). */
+DH_API int dh_decoder_meta_kv(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len);
 /* totals over all channels since creation */
 DH_API int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes);
 /* events replayed and bytes copied device->host by collect since creation */

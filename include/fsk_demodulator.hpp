@@ -1,0 +1,4 @@
+// fsk_demodulator.hpp — drop-in for the reference header of the same name (reference include/fsk_demodulator.hpp); the classes live in
+// digiham_b200_modules.hpp and run on the GPU through libdigiham_b200 (C ABI: digiham_b200.h).
+#pragma once
+#include "digiham_b200_modules.hpp"

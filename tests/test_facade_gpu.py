@@ -1,0 +1,77 @@
+"""BASELINE config 1 (plumbing): the header-compatible C++ facade modules of include/*.hpp, chained through csdr
+ring buffers by a clone of the reference's CLI loop (tests/cpp/facade_pipe.cpp), produce exactly what the CPU
+oracle's modules produce on the same one-channel input."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib
+from digiham_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+ROOT = oracle_lib.ROOT
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    d = tmp_path_factory.mktemp("facade")
+    exe = str(d / "facade_pipe")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"),
+                    "-I" + os.path.join(ROOT, "oracle", "csdr_shim"), os.path.join(ROOT, "tests", "cpp", "facade_pipe.cpp"),
+                    "-o", exe, "-L" + os.path.join(ROOT, "digiham_b200"), "-ldigiham_b200",
+                    "-Wl,-rpath," + os.path.join(ROOT, "digiham_b200")], check=True)
+    return exe, d
+
+
+def _run(harness, proto, data):
+    exe, d = harness
+    inp = str(d / (proto + ".in"))
+    data.tofile(inp)
+    prefix = str(d / proto)
+    for ext in (".out", ".meta"):
+        if os.path.exists(prefix + ext):
+            os.remove(prefix + ext)
+    subprocess.run([exe, proto, inp, prefix], check=True, stderr=subprocess.PIPE)
+    out = np.fromfile(prefix + ".out", dtype=np.uint8)
+    meta = open(prefix + ".meta", "rb").read() if os.path.exists(prefix + ".meta") else b""
+    return out, meta
+
+
+def test_facade_dmr_pipe(harness):
+    x, _ = synth.dmr_channel_bank(1, 60000, seed=31, device="cpu", noise_fraction=0.0)
+    x = x[0, :60000].numpy()
+    out, meta = _run(harness, "dmr", x)
+    _, ref_out, ref_meta = oracle_lib.best().pipe(oracle_lib.PROTO_DMR, x, chunk=128)
+    assert np.array_equal(out, ref_out) and meta == ref_meta
+    assert out.size >= 27 and b"protocol:DMR" in meta
+
+
+def test_facade_ysf_pipe(harness):
+    sym = synth.ysf_symbols(12, seed=8, mode="DN", lead_in=50)
+    x = synth.modulate(sym, sps=10, snr_db=18, rng=np.random.default_rng(1), phase=4)
+    out, meta = _run(harness, "ysf", x)
+    _, ref_out, ref_meta = oracle_lib.best().pipe(oracle_lib.PROTO_YSF, x, chunk=128)
+    assert np.array_equal(out, ref_out) and meta == ref_meta
+    assert out.size > 0 and b"mode:DN" in meta
+
+
+def test_facade_pocsag_pipe(harness):
+    bits = synth.pocsag_bits([(1234562, 3, "HELLO B200"), (42, 3, "FACADE")], seed=2, bit_errors=1)
+    x = synth.modulate(bits, sps=40, levels=synth.LEVELS2[::-1].copy(), snr_db=20, rng=np.random.default_rng(3))
+    out, meta = _run(harness, "pocsag", x)
+    _, ref_out, _ = oracle_lib.best().pipe(oracle_lib.PROTO_POCSAG, x, chunk=128)
+    assert np.array_equal(out, ref_out) and meta == b""
+    assert b"message:HELLO B200" in out.tobytes()
+
+
+def test_facade_rrc_and_dvf(harness):
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-1, 1, 5000).astype(np.float32)
+    out, _ = _run(harness, "rrc", x)
+    assert np.array_equal(out.view(np.uint32), oracle_lib.best().rrc(x, chunk=128).view(np.uint32))
+    a = rng.integers(-20000, 20000, 4000).astype(np.int16)
+    out, _ = _run(harness, "dvf", a)
+    assert np.array_equal(out.view(np.int16), oracle_lib.best().dvf(a, chunk=128))
