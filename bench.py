@@ -243,6 +243,45 @@ def main():
                "path": "dh_pipe_process_host (pinned H2D) + dh_pipe_collect (D2H + metadata replay) per step"}
     clocks = sampler.stop() if rank == 0 else None
 
+    # ---- N > 1: the two optional collectives (input scatter from an ingest rank, frame gather), measured apart ----
+    nccl = None
+    if world > 1:
+        from digiham_b200 import shard
+        pitch = x.shape[1]
+        x_all = x.repeat(world, 1) if rank == 0 else None           # ingest rank holds every rank's block
+        for _ in range(2):
+            xs = shard.scatter_channels(x_all, world * C, pitch, device=dev)
+        torch.cuda.synchronize()
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        s0.record(stream)
+        for _ in range(reps):
+            xs = shard.scatter_channels(x_all, world * C, pitch, device=dev)
+        s1.record(stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        scatter_ms = float(t.item())
+        del x_all
+        # one step on the scattered block, then gather the decoded frames + metadata on rank 0
+        pipe.process(xs, n=L)
+        pipe.collect()
+        frames = [pipe.output(c) for c in range(C)]
+        metas = [pipe.meta(c) for c in range(C)]
+        pipe.decoder.clear()
+        barrier()
+        t0 = time.perf_counter()
+        gf = shard.gather_frames(frames, world * C, device=dev)
+        gm = shard.gather_frames(metas, world * C, device=dev)
+        torch.cuda.synchronize()
+        gather_s = time.perf_counter() - t0
+        nccl = {"scatter_ms_per_step": scatter_ms,
+                "scatter_GBps_egress": (world - 1) * C * pitch * 4 / (scatter_ms * 1e-3) / 1e9,
+                "gather_ms_per_step": gather_s * 1e3,
+                "gathered_bytes": (sum(len(f) for f in gf) + sum(len(m) for m in gm)) if rank == 0 else None,
+                "note": "collectives are off the compute path: channels never interact (SURVEY.md 8e)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -303,6 +342,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+    if nccl:
+        line["nccl"] = nccl
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
