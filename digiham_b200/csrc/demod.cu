@@ -27,7 +27,7 @@
 namespace {
 
 constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (include/gfsk_demodulator.hpp:5-6)
-constexpr int kThreads = 128;
+constexpr int kThreads = 64;   // 2 warps: 6 channels per CTA at sps = 10 (39 KB smem, 5 CTAs per SM)
 constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
 
 struct ChannelState {
@@ -59,17 +59,39 @@ struct DemodParams {
 __device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
 __device__ __forceinline__ float max_gt(float cur, float v) { return v > cur ? v : cur; }
 
+// x / c for the divisors of the sps = 10 fast path, as fl32(fl64(x) * fl64(1/c)): bit-identical to the float
+// division for EVERY finite float x when c is 10 or 100 (exhaustive proof: tests/test_host_logic.py::
+// test_division_by_constant_exhaustive), and three instructions instead of the IEEE division sequence.
+__device__ __forceinline__ float div_by_const(float x, double reciprocal) {
+    return __double2float_rn(__dmul_rn((double) x, reciprocal));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dh::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// G lanes own one channel; a warp carries 32 / G channels (3 at G = 10, lanes 30 and 31 idle).
 template <int G>
-__device__ __forceinline__ unsigned group_mask() {
-    if (G == 32) return 0xffffffffu;
-    return 0xffffu << ((threadIdx.x & 31) & 16);
+struct Group {
+    static constexpr int kPerWarp = 32 / G;
+    static constexpr int kScanSteps = G > 16 ? 5 : (G > 8 ? 4 : (G > 4 ? 3 : 2));
+    static constexpr int kChunk = (kBlockSyms + G - 1) / G;
+};
+
+// inclusive-to-exclusive scan helper: value of the lane d positions below inside the group (own value if none)
+template <int G>
+__device__ __forceinline__ float group_up(unsigned gmask, float v, int d, int gl) {
+    const int lane = threadIdx.x & 31;
+    return __shfl_sync(gmask, v, gl >= d ? lane - d : lane);
 }
 
 // out_min[j] = min(src[0..j]), out_max[j] = max(FLT_MIN, src[0..j]) for j < count (count <= 100)
 template <int G>
 __device__ __forceinline__ void prefix_minmax(const float* src, int count, float* out_min, float* out_max, int gl,
                                               unsigned gmask) {
-    constexpr int chunk = (kBlockSyms + G - 1) / G;
+    constexpr int chunk = Group<G>::kChunk;
     const int j0 = gl * chunk;
     const int j1 = min(count, j0 + chunk);
     float mn = FLT_MAX, mx = FLT_MIN;
@@ -83,15 +105,15 @@ __device__ __forceinline__ void prefix_minmax(const float* src, int count, float
     float tmn = mn, tmx = mx;
 #pragma unroll
     for (int d = 1; d < G; d <<= 1) {
-        const float a = __shfl_up_sync(gmask, tmn, d, G);
-        const float b = __shfl_up_sync(gmask, tmx, d, G);
+        const float a = group_up<G>(gmask, tmn, d, gl);
+        const float b = group_up<G>(gmask, tmx, d, gl);
         if (gl >= d) {
             tmn = min_lt(tmn, a);
             tmx = max_gt(tmx, b);
         }
     }
-    float emn = __shfl_up_sync(gmask, tmn, 1, G);
-    float emx = __shfl_up_sync(gmask, tmx, 1, G);
+    float emn = group_up<G>(gmask, tmn, 1, gl);
+    float emx = group_up<G>(gmask, tmx, 1, gl);
     if (gl == 0) {
         emn = FLT_MAX;
         emx = FLT_MIN;
@@ -106,7 +128,7 @@ __device__ __forceinline__ void prefix_minmax(const float* src, int count, float
 template <int G>
 __device__ __forceinline__ void suffix_minmax_exclusive(const float* src, float* out_min, float* out_max, int gl,
                                                         unsigned gmask) {
-    constexpr int chunk = (kBlockSyms + G - 1) / G;
+    constexpr int chunk = Group<G>::kChunk;
     // work on reversed index r = 99 - j: lane owns r in [r0, r1)
     const int r0 = gl * chunk;
     const int r1 = min(kBlockSyms, r0 + chunk);
@@ -122,15 +144,15 @@ __device__ __forceinline__ void suffix_minmax_exclusive(const float* src, float*
     float tmn = mn, tmx = mx;
 #pragma unroll
     for (int d = 1; d < G; d <<= 1) {
-        const float a = __shfl_up_sync(gmask, tmn, d, G);
-        const float b = __shfl_up_sync(gmask, tmx, d, G);
+        const float a = group_up<G>(gmask, tmn, d, gl);
+        const float b = group_up<G>(gmask, tmx, d, gl);
         if (gl >= d) {
             tmn = min_lt(tmn, a);
             tmx = max_gt(tmx, b);
         }
     }
-    float emn = __shfl_up_sync(gmask, tmn, 1, G);
-    float emx = __shfl_up_sync(gmask, tmx, 1, G);
+    float emn = group_up<G>(gmask, tmn, 1, gl);
+    float emx = group_up<G>(gmask, tmx, 1, gl);
     if (gl == 0) {
         emn = FLT_MAX;
         emx = FLT_MIN;
@@ -142,17 +164,32 @@ __device__ __forceinline__ void suffix_minmax_exclusive(const float* src, float*
     }
 }
 
-template <int G>
+// number of symbols of the block starting at P that can be processed with T samples visible: symbol j starts at
+// P + j*sps + (j >= 1 ? vo : 0) and needs more than sps + 1 samples from there (gfsk_demodulator.cpp:21)
+__device__ __forceinline__ int processable(int T, int P, int vo, int sps) {
+    if (T - P < sps + 2) return 0;
+    const int room = T - P - vo - sps - 2;
+    return 1 + (room >= sps ? min(kBlockSyms - 1, room / sps) : 0);
+}
+
+// SPS > 0: compile-time samples per symbol (fast path), SPS == 0: run-time p.sps
+template <int G, int SPS>
 __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__ DemodParams p) {
     extern __shared__ __align__(16) float smem[];
+    constexpr int kPerWarp = Group<G>::kPerWarp;
     const int lane = threadIdx.x & 31;
-    const int gl = lane % G;
-    const int grp = threadIdx.x / G;
-    const int ch = blockIdx.x * (kThreads / G) + grp;
-    if (ch >= p.channels) return;   // a whole group leaves together; shuffles below only name the own group
-    const unsigned gmask = group_mask<G>();
+    const int warp = threadIdx.x >> 5;
+    const int grp_in_warp = lane / G;
+    if (grp_in_warp >= kPerWarp) return;   // lanes that do not fill a whole group (30, 31 at G = 10)
+    const int gl = lane - grp_in_warp * G;
+    const int grp = warp * kPerWarp + grp_in_warp;
+    const int ch = blockIdx.x * ((kThreads / 32) * kPerWarp) + grp;
+    if (ch >= p.channels) return;          // a whole group leaves together; shuffles below only name the own group
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
 
-    const int sps = p.sps;
+    const int sps = SPS > 0 ? SPS : p.sps;
+    const int lo = SPS == 10 ? 3 : p.lo;
+    const int hi = SPS == 10 ? 7 : p.hi;
     float* S = smem + (size_t) grp * p.group_floats;   // staged samples of the current block
     float* vol = S + p.samples_cap;                     // per-symbol volume averages of the current block
     float* avg = vol + kBlockSyms;                      // per-symbol slicer input
@@ -177,43 +214,108 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
     const int T = carry_len + p.n;              // samples visible to this call
     uint8_t* sym_row = p.sym + (size_t) ch * p.sym_pitch;
     const float fsps = (float) sps;
-    const float fwin = (float) (p.hi - p.lo);
+    const float fwin = (float) (hi - lo);
+
+    // asynchronous staging of [P, P + m*sps + 2) with aligned 16-byte copies; sample P + x lands at S[a0 + x]
+    auto stage = [&](int P, int m) {
+        const int a0 = (col0 + P) & 3;
+        const float4* src = reinterpret_cast<const float4*>(row + col0 + P - a0);
+        float4* dst = reinterpret_cast<float4*>(S);
+        const int nvec = (a0 + m * sps + 2 + 3) >> 2;
+        for (int v = gl; v < nvec; v += G) cp_async16(dst + v, src + v);
+        cp_async_commit();
+    };
 
     int P = 0;         // logical index of the current block's first window
     int emitted = 0;
-    for (;;) {
-        // symbol j of this block starts at P + j*sps + (j >= 1 ? vo : 0) and is processed iff more than
-        // sps + 1 samples are available from there (gfsk_demodulator.cpp:21)
-        int m = 0;
-        if (T - P >= sps + 2) {
-            const int room = T - P - vo - sps - 2;
-            m = 1 + (room >= sps ? min(kBlockSyms - 1, room / sps) : 0);
-        }
-        if (m <= j_done) break;
-
-        // stage [P, P + m*sps + 2) with aligned 16-byte loads; sample P + x lands at S[a0 + x]
-        const int a0 = (col0 + P) & 3;
-        {
-            const float4* src = reinterpret_cast<const float4*>(row + col0 + P - a0);
-            float4* dst = reinterpret_cast<float4*>(S);
-            const int nvec = (a0 + m * sps + 2 + 3) >> 2;
-            for (int v = gl; v < nvec; v += G) dst[v] = src[v];
-        }
+    int m = processable(T, P, vo, sps);
+    if (m > j_done) {
+        stage(P, m);
+        cp_async_wait_all();
         __syncwarp(gmask);
+    }
+    while (m > j_done) {
+        const int a0 = (col0 + P) & 3;
 
         // window sums (gfsk_demodulator.cpp:28-35, 82-83, 88)
         for (int j = gl; j < m; j += G) {
             const float* w = S + a0 + j * sps + (j ? vo : 0);
             float sum = 0.0f, vsum = 0.0f;
-            for (int i = 0; i < sps; i++) {
-                const float v = w[i];
-                if (i >= p.lo && i < p.hi) sum = __fadd_rn(sum, v);
-                vsum = __fadd_rn(vsum, v);
+            if (SPS == 10) {
+#pragma unroll
+                for (int i = 0; i < 10; i++) {
+                    const float v = w[i];
+                    if (i >= 3 && i < 7) sum = __fadd_rn(sum, v);
+                    vsum = __fadd_rn(vsum, v);
+                }
+                vol[j] = div_by_const(vsum, 1.0 / 10.0);
+                avg[j] = __fmul_rn(sum, 0.25f);   // / 4.0f, exact scaling
+            } else {
+                for (int i = 0; i < sps; i++) {
+                    const float v = w[i];
+                    if (i >= lo && i < hi) sum = __fadd_rn(sum, v);
+                    vsum = __fadd_rn(vsum, v);
+                }
+                vol[j] = __fdiv_rn(vsum, fsps);
+                avg[j] = __fdiv_rn(sum, fwin);
             }
-            vol[j] = __fdiv_rn(vsum, fsps);
-            avg[j] = __fdiv_rn(sum, fwin);
         }
-        __syncwarp(gmask);
+
+        // variance-minimum phase search over the 100 windows of a complete block (gfsk_demodulator.cpp:41-80)
+        int vo_next = 0, P_next = 0, m_next = 0;
+        const bool full = m == kBlockSyms;
+        if (full) {
+            for (int i = gl; i < sps; i += G) {
+                const float* w0 = S + a0 + i;
+                const float* wv = w0 + vo;          // windows 1..99 are shifted by the pending nudge
+                float total = __fadd_rn(0.0f, w0[0]);
+                if (SPS == 10) {
+#pragma unroll 11
+                    for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * 10]);
+                } else {
+                    for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * sps]);
+                }
+                const double mean = (double) (SPS == 10 ? div_by_const(total, 1.0 / 100.0) : __fdiv_rn(total, 100.0f));
+                double d = __dsub_rn(mean, (double) w0[0]);
+                double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
+                if (SPS == 10) {
+#pragma unroll 11
+                    for (int k = 1; k < kBlockSyms; k++) {
+                        d = __dsub_rn(mean, (double) wv[k * 10]);
+                        dsum = __dadd_rn(dsum, __dmul_rn(d, d));
+                    }
+                } else {
+                    for (int k = 1; k < kBlockSyms; k++) {
+                        d = __dsub_rn(mean, (double) wv[k * sps]);
+                        dsum = __dadd_rn(dsum, __dmul_rn(d, d));
+                    }
+                }
+                var[i] = __ddiv_rn(dsum, 100.0);
+            }
+            __syncwarp(gmask);
+            double vmin = var[0];
+            int vpos = 0;
+            for (int i = 1; i < sps; i++) {
+                const double v = var[i];
+                if (v < vmin) {
+                    vmin = v;
+                    vpos = i;
+                }
+            }
+            if (vmin <= 0 || vmin > 5000000) {
+                // no decision
+            } else if (vpos > 0 && vpos < sps / 2) {
+                vo_next = +1;
+            } else if (vpos >= sps / 2 && vpos < sps - 1) {
+                vo_next = -1;
+            }
+            // the sample buffer is free from here on: start fetching the next block while this one is sliced
+            P_next = P + kBlockSyms * sps + vo;
+            m_next = processable(T, P_next, vo_next, sps);
+            if (m_next > 0) stage(P_next, m_next);
+        } else {
+            __syncwarp(gmask);
+        }
 
         // ring min/max after symbol j = prefix over this block's volumes x suffix over the previous block's
         prefix_minmax<G>(vol, m, pmin, pmax, gl, gmask);
@@ -237,52 +339,20 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
             sym_row[emitted + (j - j_done)] = s;
         }
         emitted += m - j_done;
-        if (m < kBlockSyms) {
+        if (!full) {
             j_done = m;
             break;
         }
 
-        // variance-minimum phase search over the 100 windows of this block (gfsk_demodulator.cpp:41-80)
-        for (int i = gl; i < sps; i += G) {
-            const float* w0 = S + a0 + i;
-            float total = w0[0];
-            total = __fadd_rn(0.0f, total);
-            for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, w0[k * sps + vo]);
-            const double mean = (double) __fdiv_rn(total, 100.0f);
-            double d = __dsub_rn(mean, (double) w0[0]);
-            double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
-            for (int k = 1; k < kBlockSyms; k++) {
-                d = __dsub_rn(mean, (double) w0[k * sps + vo]);
-                dsum = __dadd_rn(dsum, __dmul_rn(d, d));
-            }
-            var[i] = __ddiv_rn(dsum, 100.0);
-        }
-        __syncwarp(gmask);
-        double vmin = var[0];
-        int vpos = 0;
-        for (int i = 1; i < sps; i++) {
-            const double v = var[i];
-            if (v < vmin) {
-                vmin = v;
-                vpos = i;
-            }
-        }
-        int vo_next = 0;
-        if (vmin <= 0 || vmin > 5000000) {
-            // no decision
-        } else if (vpos > 0 && vpos < sps / 2) {
-            vo_next = +1;
-        } else if (vpos >= sps / 2 && vpos < sps - 1) {
-            vo_next = -1;
-        }
-
         // next block
-        P += kBlockSyms * sps + vo;
+        P = P_next;
         vo = vo_next;
         j_done = 0;
+        m = m_next;
         for (int j = gl; j < kBlockSyms; j += G) prevv[j] = vol[j];
         __syncwarp(gmask);
         suffix_minmax_exclusive<G>(prevv, smin, smax, gl, gmask);
+        cp_async_wait_all();
         __syncwarp(gmask);
     }
 
@@ -448,16 +518,20 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     // samples | vol avg pmin pmax prevv smin smax | var (doubles, 8-byte aligned because all counts are even)
     p.group_floats = p.samples_cap + 7 * kBlockSyms + 2 * ((h->sps + 1) & ~1);
 
-    const int G = h->sps <= 16 ? 16 : 32;
-    const int groups = kThreads / G;
+    // lanes per channel: 10 on the sps = 10 fast path (3 channels per warp), else 16 or 32
+    const int G = h->sps == 10 ? 10 : (h->sps <= 16 ? 16 : 32);
+    const int groups = (kThreads / 32) * (32 / G);
     const unsigned grid = (h->channels + groups - 1) / groups;
     const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
-    if (G == 16) {
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        demod_kernel<16><<<grid, kThreads, smem, st>>>(p);
+    if (G == 10) {
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        demod_kernel<10, 10><<<grid, kThreads, smem, st>>>(p);
+    } else if (G == 16) {
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        demod_kernel<16, 0><<<grid, kThreads, smem, st>>>(p);
     } else {
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        demod_kernel<32><<<grid, kThreads, smem, st>>>(p);
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+        demod_kernel<32, 0><<<grid, kThreads, smem, st>>>(p);
     }
     DH_CUDA(cudaGetLastError());
     return DH_OK;

@@ -100,6 +100,48 @@ def test_reciprocal_gain_exhaustive():
     assert int(out.strip()) == 0
 
 
+DIVC_SRC = r"""
+#include <stdio.h>
+#include <stdint.h>
+#include <string.h>
+#include <math.h>
+int main(void) {
+    const float cs[2] = {10.0f, 100.0f};
+    unsigned long long bad = 0;
+    for (int g = 0; g < 2; g++) {
+        const float c = cs[g];
+        const double rc = 1.0 / (double) c;
+        #pragma omp parallel for reduction(+:bad) schedule(static)
+        for (long long b = 0; b < (1LL << 32); b += STRIDE) {
+            uint32_t u = (uint32_t) b, r1, r2; float x, q1, q2;
+            memcpy(&x, &u, 4);
+            if (isnan(x)) continue;
+            q1 = x / c;                            /* reference: volume_sum / samplesPerSymbol, total / 100 */
+            q2 = (float) ((double) x * rc);        /* K2 fast path */
+            memcpy(&r1, &q1, 4); memcpy(&r2, &q2, 4);
+            if (r1 != r2) bad++;
+        }
+    }
+    printf("%llu\n", bad);
+    return 0;
+}
+"""
+
+
+def test_division_by_constant_exhaustive():
+    """K2's sps = 10 path computes x / 10 and x / 100 as fl32(fl64(x) * fl64(1/c)); identical to the float division
+    of the reference (gfsk_demodulator.cpp:53,82) for EVERY float32 x (DH_FAST_TESTS=1 samples every 7th)."""
+    stride = 7 if os.environ.get("DH_FAST_TESTS") else 1
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "divc.c")
+        open(src, "w").write(DIVC_SRC)
+        exe = os.path.join(d, "divc")
+        subprocess.run(["gcc", "-O2", "-fopenmp", "-ffp-contract=off", "-DSTRIDE=%d" % stride, src, "-o", exe, "-lm"],
+                       check=True)
+        out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert int(out.strip()) == 0
+
+
 def _events(recs):
     buf = bytearray()
     for kind, slot, a, b, data in recs:
