@@ -39,7 +39,8 @@ struct ChannelState {
 };
 
 struct DemodParams {
-    float* work;                 // [channels][pitch]; chunk sample 0 sits at column carry_cap
+    const float* work;           // [channels][pitch] rows read by this call; chunk sample 0 at column carry_cap
+    float* work_next;            // rows the next call reads: receives the carried tail
     unsigned long long pitch;
     uint8_t* sym;                // [channels][sym_pitch]
     unsigned long long sym_pitch;
@@ -72,95 +73,86 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-// G lanes own one channel; a warp carries 32 / G channels (3 at G = 10, lanes 30 and 31 idle).
+// G lanes own one channel; a warp carries 32 / G channels (3 at G = 10, lanes 30 and 31 idle).  Lane gl owns the
+// kChunk consecutive symbols [gl * kChunk, (gl + 1) * kChunk) of every 100-symbol block.
 template <int G>
 struct Group {
     static constexpr int kPerWarp = 32 / G;
-    static constexpr int kScanSteps = G > 16 ? 5 : (G > 8 ? 4 : (G > 4 ? 3 : 2));
     static constexpr int kChunk = (kBlockSyms + G - 1) / G;
 };
 
-// inclusive-to-exclusive scan helper: value of the lane d positions below inside the group (own value if none)
-template <int G>
+// value held by the lane d positions below / above inside the group (own value when there is none)
 __device__ __forceinline__ float group_up(unsigned gmask, float v, int d, int gl) {
     const int lane = threadIdx.x & 31;
     return __shfl_sync(gmask, v, gl >= d ? lane - d : lane);
 }
-
-// out_min[j] = min(src[0..j]), out_max[j] = max(FLT_MIN, src[0..j]) for j < count (count <= 100)
 template <int G>
-__device__ __forceinline__ void prefix_minmax(const float* src, int count, float* out_min, float* out_max, int gl,
-                                              unsigned gmask) {
-    constexpr int chunk = Group<G>::kChunk;
-    const int j0 = gl * chunk;
-    const int j1 = min(count, j0 + chunk);
-    float mn = FLT_MAX, mx = FLT_MIN;
-    for (int j = j0; j < j1; j++) {
-        const float v = src[j];
-        mn = min_lt(mn, v);
-        mx = max_gt(mx, v);
-        out_min[j] = mn;
-        out_max[j] = mx;
-    }
+__device__ __forceinline__ float group_down(unsigned gmask, float v, int d, int gl) {
+    const int lane = threadIdx.x & 31;
+    return __shfl_sync(gmask, v, gl + d < G ? lane + d : lane);
+}
+
+// exclusive scans of per-lane (min, max) totals across the group: up = over lower lanes, down = over higher lanes
+template <int G>
+__device__ __forceinline__ void exclusive_up(unsigned gmask, int gl, float& mn, float& mx) {
     float tmn = mn, tmx = mx;
 #pragma unroll
     for (int d = 1; d < G; d <<= 1) {
-        const float a = group_up<G>(gmask, tmn, d, gl);
-        const float b = group_up<G>(gmask, tmx, d, gl);
+        const float a = group_up(gmask, tmn, d, gl);
+        const float b = group_up(gmask, tmx, d, gl);
         if (gl >= d) {
             tmn = min_lt(tmn, a);
             tmx = max_gt(tmx, b);
         }
     }
-    float emn = group_up<G>(gmask, tmn, 1, gl);
-    float emx = group_up<G>(gmask, tmx, 1, gl);
+    mn = group_up(gmask, tmn, 1, gl);
+    mx = group_up(gmask, tmx, 1, gl);
     if (gl == 0) {
-        emn = FLT_MAX;
-        emx = FLT_MIN;
+        mn = FLT_MAX;
+        mx = FLT_MIN;
     }
-    for (int j = j0; j < j1; j++) {
-        out_min[j] = min_lt(out_min[j], emn);
-        out_max[j] = max_gt(out_max[j], emx);
+}
+template <int G>
+__device__ __forceinline__ void exclusive_down(unsigned gmask, int gl, float& mn, float& mx) {
+    float tmn = mn, tmx = mx;
+#pragma unroll
+    for (int d = 1; d < G; d <<= 1) {
+        const float a = group_down<G>(gmask, tmn, d, gl);
+        const float b = group_down<G>(gmask, tmx, d, gl);
+        if (gl + d < G) {
+            tmn = min_lt(tmn, a);
+            tmx = max_gt(tmx, b);
+        }
+    }
+    mn = group_down<G>(gmask, tmn, 1, gl);
+    mx = group_down<G>(gmask, tmx, 1, gl);
+    if (gl == G - 1) {
+        mn = FLT_MAX;
+        mx = FLT_MIN;
     }
 }
 
-// out_min[j] = min(src[j+1..99]), out_max[j] = max(FLT_MIN, src[j+1..99]); empty range -> FLT_MAX / FLT_MIN
+// smn[q] / smx[q] = min / max(FLT_MIN, .) over the previous block's volumes of all symbols AFTER symbol
+// gl * kChunk + q (empty range -> FLT_MAX / FLT_MIN): the part of the 100-entry ring the current block has not
+// overwritten yet when its symbol j is sliced
 template <int G>
-__device__ __forceinline__ void suffix_minmax_exclusive(const float* src, float* out_min, float* out_max, int gl,
-                                                        unsigned gmask) {
-    constexpr int chunk = Group<G>::kChunk;
-    // work on reversed index r = 99 - j: lane owns r in [r0, r1)
-    const int r0 = gl * chunk;
-    const int r1 = min(kBlockSyms, r0 + chunk);
+__device__ __forceinline__ void suffix_of_previous(const float* pv, float* smn, float* smx, int gl, unsigned gmask) {
+    constexpr int CH = Group<G>::kChunk;
     float mn = FLT_MAX, mx = FLT_MIN;
-    for (int r = r0; r < r1; r++) {
-        // exclusive: store before absorbing src[99 - r]
-        out_min[kBlockSyms - 1 - r] = mn;
-        out_max[kBlockSyms - 1 - r] = mx;
-        const float v = src[kBlockSyms - 1 - r];
-        mn = min_lt(mn, v);
-        mx = max_gt(mx, v);
-    }
-    float tmn = mn, tmx = mx;
 #pragma unroll
-    for (int d = 1; d < G; d <<= 1) {
-        const float a = group_up<G>(gmask, tmn, d, gl);
-        const float b = group_up<G>(gmask, tmx, d, gl);
-        if (gl >= d) {
-            tmn = min_lt(tmn, a);
-            tmx = max_gt(tmx, b);
+    for (int q = CH - 1; q >= 0; q--) {
+        smn[q] = mn;
+        smx[q] = mx;
+        if (gl * CH + q < kBlockSyms) {
+            mn = min_lt(mn, pv[q]);
+            mx = max_gt(mx, pv[q]);
         }
     }
-    float emn = group_up<G>(gmask, tmn, 1, gl);
-    float emx = group_up<G>(gmask, tmx, 1, gl);
-    if (gl == 0) {
-        emn = FLT_MAX;
-        emx = FLT_MIN;
-    }
-    for (int r = r0; r < r1; r++) {
-        const int j = kBlockSyms - 1 - r;
-        out_min[j] = min_lt(out_min[j], emn);
-        out_max[j] = max_gt(out_max[j], emx);
+    exclusive_down<G>(gmask, gl, mn, mx);
+#pragma unroll
+    for (int q = 0; q < CH; q++) {
+        smn[q] = min_lt(smn[q], mn);
+        smx[q] = max_gt(smx[q], mx);
     }
 }
 
@@ -177,6 +169,7 @@ template <int G, int SPS>
 __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__ DemodParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kPerWarp = Group<G>::kPerWarp;
+    constexpr int CH = Group<G>::kChunk;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int grp_in_warp = lane / G;
@@ -190,26 +183,20 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
     const int sps = SPS > 0 ? SPS : p.sps;
     const int lo = SPS == 10 ? 3 : p.lo;
     const int hi = SPS == 10 ? 7 : p.hi;
-    float* S = smem + (size_t) grp * p.group_floats;   // staged samples of the current block
-    float* vol = S + p.samples_cap;                     // per-symbol volume averages of the current block
-    float* avg = vol + kBlockSyms;                      // per-symbol slicer input
-    float* pmin = avg + kBlockSyms;
-    float* pmax = pmin + kBlockSyms;
-    float* prevv = pmax + kBlockSyms;                   // volumes of the previous block
-    float* smin = prevv + kBlockSyms;
-    float* smax = smin + kBlockSyms;
-    double* var = reinterpret_cast<double*>(smax + kBlockSyms);   // [sps]
+    float* S = smem + (size_t) grp * p.group_floats;                 // staged samples of the current block
+    double* var = reinterpret_cast<double*>(S + p.samples_cap);     // [sps] phase variances
 
     ChannelState* st = p.state + ch;
     int vo = st->vo;
     int j_done = st->j_done;
     const int carry_len = st->carry_len;
-    for (int j = gl; j < kBlockSyms; j += G) prevv[j] = st->vol_prev[j];
-    __syncwarp(gmask);
-    suffix_minmax_exclusive<G>(prevv, smin, smax, gl, gmask);
-    __syncwarp(gmask);
+    const int j_first = gl * CH;           // first symbol of every block this lane owns
+    float pv[CH], smn[CH], smx[CH];        // previous block's volumes and their exclusive suffix min / max
+#pragma unroll
+    for (int q = 0; q < CH; q++) pv[q] = j_first + q < kBlockSyms ? st->vol_prev[j_first + q] : 0.0f;
+    suffix_of_previous<G>(pv, smn, smx, gl, gmask);
 
-    float* row = p.work + (size_t) ch * p.pitch;
+    const float* row = p.work + (size_t) ch * p.pitch;
     const int col0 = p.carry_cap - carry_len;   // column of logical stream index 0
     const int T = carry_len + p.n;              // samples visible to this call
     uint8_t* sym_row = p.sym + (size_t) ch * p.sym_pitch;
@@ -237,27 +224,34 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
     while (m > j_done) {
         const int a0 = (col0 + P) & 3;
 
-        // window sums (gfsk_demodulator.cpp:28-35, 82-83, 88)
-        for (int j = gl; j < m; j += G) {
-            const float* w = S + a0 + j * sps + (j ? vo : 0);
-            float sum = 0.0f, vsum = 0.0f;
-            if (SPS == 10) {
+        // window sums of the symbols this lane owns (gfsk_demodulator.cpp:28-35, 82-83, 88)
+        float volr[CH], avgr[CH];
 #pragma unroll
-                for (int i = 0; i < 10; i++) {
-                    const float v = w[i];
-                    if (i >= 3 && i < 7) sum = __fadd_rn(sum, v);
-                    vsum = __fadd_rn(vsum, v);
+        for (int q = 0; q < CH; q++) {
+            const int j = j_first + q;
+            volr[q] = 0.0f;
+            avgr[q] = 0.0f;
+            if (j < m) {
+                const float* w = S + a0 + j * sps + (j ? vo : 0);
+                float sum = 0.0f, vsum = 0.0f;
+                if (SPS == 10) {
+#pragma unroll
+                    for (int i = 0; i < 10; i++) {
+                        const float v = w[i];
+                        if (i >= 3 && i < 7) sum = __fadd_rn(sum, v);
+                        vsum = __fadd_rn(vsum, v);
+                    }
+                    volr[q] = div_by_const(vsum, 1.0 / 10.0);
+                    avgr[q] = __fmul_rn(sum, 0.25f);   // / 4.0f, exact scaling
+                } else {
+                    for (int i = 0; i < sps; i++) {
+                        const float v = w[i];
+                        if (i >= lo && i < hi) sum = __fadd_rn(sum, v);
+                        vsum = __fadd_rn(vsum, v);
+                    }
+                    volr[q] = __fdiv_rn(vsum, fsps);
+                    avgr[q] = __fdiv_rn(sum, fwin);
                 }
-                vol[j] = div_by_const(vsum, 1.0 / 10.0);
-                avg[j] = __fmul_rn(sum, 0.25f);   // / 4.0f, exact scaling
-            } else {
-                for (int i = 0; i < sps; i++) {
-                    const float v = w[i];
-                    if (i >= lo && i < hi) sum = __fadd_rn(sum, v);
-                    vsum = __fadd_rn(vsum, v);
-                }
-                vol[j] = __fdiv_rn(vsum, fsps);
-                avg[j] = __fdiv_rn(sum, fwin);
             }
         }
 
@@ -312,31 +306,50 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
             // the sample buffer is free from here on: start fetching the next block while this one is sliced
             P_next = P + kBlockSyms * sps + vo;
             m_next = processable(T, P_next, vo_next, sps);
-            if (m_next > 0) stage(P_next, m_next);
-        } else {
             __syncwarp(gmask);
+            if (m_next > 0) stage(P_next, m_next);
         }
 
-        // ring min/max after symbol j = prefix over this block's volumes x suffix over the previous block's
-        prefix_minmax<G>(vol, m, pmin, pmax, gl, gmask);
-        __syncwarp(gmask);
+        // Ring min/max right after symbol j was pushed = (this block's volumes 0..j) x (previous block's volumes
+        // j+1..99).  Prefix part: running min/max over the own symbols on top of the exclusive scan over the lower
+        // lanes; only valid symbols (j < m) take part.
+        float emn = FLT_MAX, emx = FLT_MIN;
+#pragma unroll
+        for (int q = 0; q < CH; q++) {
+            if (j_first + q < m) {
+                emn = min_lt(emn, volr[q]);
+                emx = max_gt(emx, volr[q]);
+            }
+        }
+        exclusive_up<G>(gmask, gl, emn, emx);
 
         // calibrateAudio + slicing (gfsk_demodulator.cpp:88-104, 109-122)
-        for (int j = j_done + gl; j < m; j += G) {
-            const float mn = min_lt(pmin[j], smin[j]);
-            const float mx = max_gt(pmax[j], smax[j]);
-            const float center = __fmul_rn(__fadd_rn(mx, mn), 0.5f);
-            const float a = avg[j];
-            uint8_t s;
-            if (p.four_level) {
-                const double c = (double) center;
-                const float umid = __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mx, center), 0.625), c));
-                const float lmid = __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mn, center), 0.625), c));
-                s = a > center ? (a > umid ? 1 : 0) : (a < lmid ? 3 : 2);
-            } else {
-                s = a > center ? (p.invert ? 0 : 1) : (p.invert ? 1 : 0);
+        float rmn = emn, rmx = emx;
+#pragma unroll
+        for (int q = 0; q < CH; q++) {
+            const int j = j_first + q;
+            if (j < m) {
+                rmn = min_lt(rmn, volr[q]);
+                rmx = max_gt(rmx, volr[q]);
+                if (j >= j_done) {
+                    const float mn = min_lt(rmn, smn[q]);
+                    const float mx = max_gt(rmx, smx[q]);
+                    const float center = __fmul_rn(__fadd_rn(mx, mn), 0.5f);
+                    const float a = avgr[q];
+                    uint8_t s;
+                    if (p.four_level) {
+                        const double c = (double) center;
+                        const float umid =
+                            __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mx, center), 0.625), c));
+                        const float lmid =
+                            __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mn, center), 0.625), c));
+                        s = a > center ? (a > umid ? 1 : 0) : (a < lmid ? 3 : 2);
+                    } else {
+                        s = a > center ? (p.invert ? 0 : 1) : (p.invert ? 1 : 0);
+                    }
+                    sym_row[emitted + (j - j_done)] = s;
+                }
             }
-            sym_row[emitted + (j - j_done)] = s;
         }
         emitted += m - j_done;
         if (!full) {
@@ -344,33 +357,30 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
             break;
         }
 
-        // next block
+        // next block: this block's volumes become the "previous" ring content
         P = P_next;
         vo = vo_next;
         j_done = 0;
         m = m_next;
-        for (int j = gl; j < kBlockSyms; j += G) prevv[j] = vol[j];
-        __syncwarp(gmask);
-        suffix_minmax_exclusive<G>(prevv, smin, smax, gl, gmask);
+#pragma unroll
+        for (int q = 0; q < CH; q++) pv[q] = volr[q];
+        suffix_of_previous<G>(pv, smn, smx, gl, gmask);
         cp_async_wait_all();
         __syncwarp(gmask);
     }
 
-    // carry: state + the unconsumed tail [P, T) moved right-aligned in front of column carry_cap
-    for (int j = gl; j < kBlockSyms; j += G) st->vol_prev[j] = prevv[j];
+    // carry: state + the unconsumed tail [P, T), written right-aligned in front of column carry_cap of the row
+    // the NEXT call reads (the two work buffers alternate so that the producer of the next chunk can already
+    // run while this kernel is still reading the current one)
+#pragma unroll
+    for (int q = 0; q < CH; q++) {
+        if (j_first + q < kBlockSyms) st->vol_prev[j_first + q] = pv[q];
+    }
     const int keep = T - P;
     {
         const float* src = row + col0 + P;
-        float* dst = row + p.carry_cap - keep;
-        if (dst != src) {
-            for (int o = 0; o < keep; o += G) {
-                const int idx = o + gl;
-                const float v = idx < keep ? src[idx] : 0.0f;
-                __syncwarp(gmask);
-                if (idx < keep) dst[idx] = v;
-                __syncwarp(gmask);
-            }
-        }
+        float* dst = p.work_next + (size_t) ch * p.pitch + p.carry_cap - keep;
+        for (int idx = gl; idx < keep; idx += G) dst[idx] = src[idx];
     }
     if (gl == 0) {
         st->vo = vo;
@@ -391,7 +401,8 @@ struct dh_demod {
     int lo = 0, hi = 0;
     int carry_cap = 0;
     ChannelState* d_state = nullptr;
-    float* d_work = nullptr;
+    float* d_work[2] = {nullptr, nullptr};   // alternate per call (see demod_kernel carry)
+    int cur = 0;
     size_t pitch = 0;      // elements per work row
     size_t max_n = 0;      // chunk capacity of the work rows
 };
@@ -399,21 +410,24 @@ struct dh_demod {
 namespace {
 
 int demod_reserve(dh_demod* h, size_t max_n) {
-    if (h->d_work && max_n <= h->max_n) return DH_OK;
+    if (h->d_work[0] && max_n <= h->max_n) return DH_OK;
     const size_t n4 = (max_n + 3) & ~(size_t) 3;
     const size_t pitch = (size_t) h->carry_cap + n4;
-    float* nw = nullptr;
-    DH_CUDA(cudaMalloc(&nw, (size_t) h->channels * pitch * sizeof(float)));
-    if (h->d_work) {
-        // keep the carried tails; the bank may be mid-stream
-        DH_CUDA(cudaDeviceSynchronize());
-        DH_CUDA(cudaMemcpy2D(nw, pitch * sizeof(float), h->d_work, h->pitch * sizeof(float),
-                             (size_t) h->carry_cap * sizeof(float), h->channels, cudaMemcpyDeviceToDevice));
-        DH_CUDA(cudaFree(h->d_work));
-    } else {
-        DH_CUDA(cudaMemset(nw, 0, (size_t) h->channels * pitch * sizeof(float)));
+    float* nw[2] = {nullptr, nullptr};
+    for (int b = 0; b < 2; b++) {
+        DH_CUDA(cudaMalloc(&nw[b], (size_t) h->channels * pitch * sizeof(float)));
+        DH_CUDA(cudaMemset(nw[b], 0, (size_t) h->channels * pitch * sizeof(float)));
     }
-    h->d_work = nw;
+    if (h->d_work[0]) {
+        // keep the carried tails (they live in the buffer the next call reads); the bank may be mid-stream
+        DH_CUDA(cudaDeviceSynchronize());
+        DH_CUDA(cudaMemcpy2D(nw[h->cur], pitch * sizeof(float), h->d_work[h->cur], h->pitch * sizeof(float),
+                             (size_t) h->carry_cap * sizeof(float), h->channels, cudaMemcpyDeviceToDevice));
+        DH_CUDA(cudaFree(h->d_work[0]));
+        DH_CUDA(cudaFree(h->d_work[1]));
+    }
+    h->d_work[0] = nw[0];
+    h->d_work[1] = nw[1];
     h->pitch = pitch;
     h->max_n = n4;
     return DH_OK;
@@ -465,7 +479,7 @@ int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch) {
     dh::DeviceGuard guard(h->device);
     int rc = demod_reserve(h, max_n);
     if (rc != DH_OK) return rc;
-    if (d_buf) *d_buf = h->d_work + h->carry_cap;
+    if (d_buf) *d_buf = h->d_work[h->cur] + h->carry_cap;
     if (pitch) *pitch = h->pitch;
     return DH_OK;
 }
@@ -490,17 +504,19 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     DH_REQUIRE(sym_pitch >= dh_demod_max_symbols(h, n), DH_E_INVALID,
                "dh_demod_process: sym_pitch %zu too small, need dh_demod_max_symbols(n) = %zu", sym_pitch,
                dh_demod_max_symbols(h, n));
-    const bool zero_copy = h->d_work && d_in == h->d_work + h->carry_cap && in_pitch == h->pitch && n <= h->max_n;
+    const bool zero_copy =
+        h->d_work[0] && d_in == h->d_work[h->cur] + h->carry_cap && in_pitch == h->pitch && n <= h->max_n;
     if (!zero_copy) {
         DH_REQUIRE(in_pitch >= n, DH_E_INVALID, "dh_demod_process: in_pitch < n");
         int rc = demod_reserve(h, n);
         if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->d_work + h->carry_cap, h->pitch * sizeof(float), d_in, in_pitch * sizeof(float),
+        DH_CUDA(cudaMemcpy2DAsync(h->d_work[h->cur] + h->carry_cap, h->pitch * sizeof(float), d_in, in_pitch * sizeof(float),
                                   n * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, st));
     }
 
     DemodParams p;
-    p.work = h->d_work;
+    p.work = h->d_work[h->cur];
+    p.work_next = h->d_work[h->cur ^ 1];
     p.pitch = h->pitch;
     p.sym = d_sym;
     p.sym_pitch = sym_pitch;
@@ -515,8 +531,8 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     p.invert = h->invert;
     p.carry_cap = h->carry_cap;
     p.samples_cap = (kBlockSyms * h->sps + 2 + 3 + 3 + 3) & ~3;
-    // samples | vol avg pmin pmax prevv smin smax | var (doubles, 8-byte aligned because all counts are even)
-    p.group_floats = p.samples_cap + 7 * kBlockSyms + 2 * ((h->sps + 1) & ~1);
+    // samples | var (doubles; 8-byte aligned because samples_cap is a multiple of 4)
+    p.group_floats = p.samples_cap + 2 * ((h->sps + 1) & ~1);
 
     // lanes per channel: 10 on the sps = 10 fast path (3 channels per warp), else 16 or 32
     const int G = h->sps == 10 ? 10 : (h->sps <= 16 ? 16 : 32);
@@ -534,6 +550,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         demod_kernel<32, 0><<<grid, kThreads, smem, st>>>(p);
     }
     DH_CUDA(cudaGetLastError());
+    h->cur ^= 1;   // the carried tails now sit in the other buffer
     return DH_OK;
 }
 
@@ -548,7 +565,8 @@ void dh_demod_destroy(dh_demod* h) {
     if (!h) return;
     dh::DeviceGuard guard(h->device);
     cudaFree(h->d_state);
-    cudaFree(h->d_work);
+    cudaFree(h->d_work[0]);
+    cudaFree(h->d_work[1]);
     delete h;
 }
 

@@ -92,6 +92,9 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
     int rc = mark();
     if (rc != DH_OK) return rc;
     if (h->rrc) {
+        // the demodulator's input rows alternate between two buffers from call to call
+        rc = dh_demod_reserve(h->demod, h->max_chunk, &h->d_filt, &h->filt_pitch);
+        if (rc != DH_OK) return rc;
         rc = dh_rrc_process(h->rrc, d_in, in_pitch, h->d_filt, h->filt_pitch, n, stream);
         if (rc != DH_OK) return rc;
         h->launches++;

@@ -102,8 +102,9 @@ typedef struct dh_demod dh_demod;
 DH_API int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_level, uint32_t sps, int invert);
 /* Zero-copy input: returns the device address (row of channel 0) and pitch where a producer such as
  * dh_rrc_process should write the next block of up to max_n samples per channel.  Passing exactly this
- * pointer/pitch to dh_demod_process skips the staging copy.  The address stays valid until a reserve or
- * process call needs a larger max_n. */
+ * pointer/pitch to dh_demod_process skips the staging copy.  The bank alternates between two sets of rows from
+ * one process call to the next (so that the producer of chunk k+1 may run while chunk k is still being
+ * demodulated): query the address again before every producer call. */
 DH_API int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch);
 /* upper bound of the symbols one dh_demod_process call with n samples can emit per channel */
 DH_API size_t dh_demod_max_symbols(const dh_demod* h, size_t n);

@@ -128,10 +128,10 @@ def test_demod_zero_copy_from_rrc():
     rrc = dh.RrcBank(C, dh.RRC_WIDE)
     dem = dh.DemodBank(C, sps=10)
     chunk = 7000
-    ptr, pitch = dem.reserve(chunk)
     outs = [[] for _ in range(C)]
     for pos in range(0, n, chunk):
         c = min(chunk, n - pos)
+        ptr, pitch = dem.reserve(chunk)      # the input rows alternate from call to call
         blk = np.zeros((C, (c + 3) & ~3), dtype=np.float32)
         blk[:, :c] = raw[:, pos:pos + c]
         d = torch.from_numpy(blk).cuda()
