@@ -289,7 +289,8 @@ def main():
 
     # ---- roofline of the dominant kernel (K1) ------------------------------------------------------------------
     peak, peak_src = peaks()
-    k1_ms = stage_ms[0] / max(1, calls)
+    # stage sums cover every (sub-)chunk launch of the timed region; per step = / steps
+    k1_ms = stage_ms[0] / args.steps
     achieved = C * L * ALGO_BYTES_PER_SAMPLE_K1 / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -301,9 +302,12 @@ def main():
     roofline = {"bound": "hbm", "kernel": "rrc_fir_kernel<80> (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_K1,
-                "ms_per_launch": k1_ms,
-                "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / max(1, calls),
-                                      "k3_k4_dmr": stage_ms[2] / max(1, calls)},
+                "ms_per_launch": k1_ms * args.steps / max(1, calls), "k1_ms_per_step": k1_ms,
+                "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / args.steps,
+                                      "k3_k4_dmr": stage_ms[2] / args.steps,
+                                      "launches_per_stage_per_step": calls / args.steps,
+                                      "note": "stages of consecutive sub-chunks overlap on two streams, so the "
+                                              "sum exceeds ms_per_step"},
                 "fp32_issue_bound": {"note": "K1 executes 162 separately rounded fp32 ops/sample (no FMA, bit-exact); "
                                              "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
                                      "fp32_ops_per_s": C * L * 162 / (k1_ms * 1e-3) if k1_ms > 0 else None,

@@ -84,6 +84,7 @@ def lib():
     L.dh_pipe_last_symbols.argtypes = [ctypes.c_void_p, c_void_pp, ctypes.POINTER(ctypes.c_size_t), c_void_pp]
     L.dh_pipe_read_symbols.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                        ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_pipe_set_sub_chunk.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.dh_pipe_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.dh_pipe_stage_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     L.dh_pipe_launch_count.argtypes = [ctypes.c_void_p]
@@ -333,6 +334,10 @@ class Pipe:
 
     def collect(self, stream=None):
         check(lib().dh_pipe_collect(self._h, _stream_ptr(stream)))
+
+    def set_sub_chunk(self, sub_chunk):
+        """Software pipelining granularity inside one process call (0 = three kernels back to back)."""
+        check(lib().dh_pipe_set_sub_chunk(self._h, int(sub_chunk)))
 
     def set_profiling(self, enable):
         check(lib().dh_pipe_set_profiling(self._h, int(enable)))

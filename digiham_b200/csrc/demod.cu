@@ -70,6 +70,9 @@ __device__ __forceinline__ float div_by_const(float x, double reciprocal) {
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dh::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dh::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
@@ -378,9 +381,15 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
     }
     const int keep = T - P;
     {
+        // through the (now idle) sample buffer, so that all loads are in flight at once instead of one
+        // load->store round trip per element
         const float* src = row + col0 + P;
         float* dst = p.work_next + (size_t) ch * p.pitch + p.carry_cap - keep;
-        for (int idx = gl; idx < keep; idx += G) dst[idx] = src[idx];
+        for (int idx = gl; idx < keep; idx += G) cp_async4(S + idx, src + idx);
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp(gmask);
+        for (int idx = gl; idx < keep; idx += G) dst[idx] = S[idx];
     }
     if (gl == 0) {
         st->vo = vo;

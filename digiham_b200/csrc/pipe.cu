@@ -28,10 +28,17 @@ struct dh_pipe {
     uint32_t* d_nsym = nullptr;
     float* d_stage = nullptr;     // device staging for host input
     size_t stage_pitch = 0;
-    // optional per-stage device timing (CUDA events on the caller's stream)
+    // optional per-stage device timing: CUDA events around every kernel, on the stream it is launched on
     bool profiling = false;
-    std::vector<cudaEvent_t> events;   // 4 per process call: start, after K1, after K2, after decoder
+    std::vector<cudaEvent_t> events;   // groups of 6: K1 start/end, K2 start/end, decoder start/end
     uint64_t launches = 0;             // kernels launched by this pipe since creation
+    // Software pipelining inside one process call: the chunk is cut into sub-chunks; K1 of sub-chunk c+1 (stream
+    // a) overlaps K2 + decoder of sub-chunk c (stream b, higher priority).  K1 is issue-bound, K2 and the decoder
+    // are latency-bound sequential walks, so together they fill the SMs.
+    size_t sub_chunk = 0;              // 0 = no pipelining (default: measured slower on B200)
+    cudaStream_t sa = nullptr, sb = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_done = nullptr;
+    std::vector<cudaEvent_t> ev_k1, ev_k2;
 };
 
 extern "C" {
@@ -61,7 +68,13 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
     }
     if (rc == DH_OK) {
         dh::DeviceGuard guard(device);
-        cudaError_t e = cudaMalloc(&h->d_nsym, (size_t) channels * sizeof(uint32_t));
+        int lo_prio = 0, hi_prio = 0;
+        cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
+        cudaError_t e = cudaStreamCreateWithPriority(&h->sa, cudaStreamNonBlocking, lo_prio);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi_prio);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_nsym, (size_t) channels * sizeof(uint32_t));
         if (e != cudaSuccess) {
             dh::set_error("dh_pipe_create: %s", cudaGetErrorString(e));
             rc = (int) e;
@@ -75,42 +88,94 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
     return DH_OK;
 }
 
-int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream) {
-    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_device: handle is NULL");
-    DH_REQUIRE(n <= h->max_chunk, DH_E_INVALID, "dh_pipe_process_device: n=%zu exceeds max_chunk=%zu", n, h->max_chunk);
-    if (n == 0) return DH_OK;
-    cudaStream_t st = (cudaStream_t) stream;
-    auto mark = [&]() -> int {
+namespace {
+
+// one sub-chunk through the three stages; k1/k23 are the streams of K1 and of K2 + decoder
+int run_stages(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, cudaStream_t k1, cudaStream_t k23,
+               cudaEvent_t k1_done, cudaEvent_t k2_done) {
+    auto mark = [&](cudaStream_t st) -> int {
         if (!h->profiling) return DH_OK;
-        dh::DeviceGuard guard(h->device);
         cudaEvent_t e;
         DH_CUDA(cudaEventCreate(&e));
         DH_CUDA(cudaEventRecord(e, st));
         h->events.push_back(e);
         return DH_OK;
     };
-    int rc = mark();
-    if (rc != DH_OK) return rc;
+    int rc;
     if (h->rrc) {
         // the demodulator's input rows alternate between two buffers from call to call
         rc = dh_demod_reserve(h->demod, h->max_chunk, &h->d_filt, &h->filt_pitch);
         if (rc != DH_OK) return rc;
-        rc = dh_rrc_process(h->rrc, d_in, in_pitch, h->d_filt, h->filt_pitch, n, stream);
+        if ((rc = mark(k1)) != DH_OK) return rc;
+        rc = dh_rrc_process(h->rrc, d_in, in_pitch, h->d_filt, h->filt_pitch, n, k1);
         if (rc != DH_OK) return rc;
         h->launches++;
-        if ((rc = mark()) != DH_OK) return rc;
-        rc = dh_demod_process(h->demod, h->d_filt, h->filt_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, stream);
+        if ((rc = mark(k1)) != DH_OK) return rc;
+        if (k1 != k23) {
+            DH_CUDA(cudaEventRecord(k1_done, k1));
+            DH_CUDA(cudaStreamWaitEvent(k23, k1_done, 0));
+        }
+        if ((rc = mark(k23)) != DH_OK) return rc;
+        rc = dh_demod_process(h->demod, h->d_filt, h->filt_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, k23);
     } else {
-        if ((rc = mark()) != DH_OK) return rc;
-        rc = dh_demod_process(h->demod, d_in, in_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, stream);
+        if ((rc = mark(k1)) != DH_OK) return rc;
+        if ((rc = mark(k1)) != DH_OK) return rc;
+        if ((rc = mark(k23)) != DH_OK) return rc;
+        rc = dh_demod_process(h->demod, d_in, in_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, k23);
     }
     if (rc != DH_OK) return rc;
     h->launches++;
-    if ((rc = mark()) != DH_OK) return rc;
-    rc = dh_decoder_process(h->decoder, h->d_sym, h->sym_pitch, h->d_nsym, h->max_syms, stream);
+    if ((rc = mark(k23)) != DH_OK) return rc;
+    if (k2_done) DH_CUDA(cudaEventRecord(k2_done, k23));
+    if ((rc = mark(k23)) != DH_OK) return rc;
+    rc = dh_decoder_process(h->decoder, h->d_sym, h->sym_pitch, h->d_nsym, h->max_syms, k23);
     if (rc != DH_OK) return rc;
     h->launches++;
-    return mark();
+    return mark(k23);
+}
+
+}  // namespace
+
+int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_device: handle is NULL");
+    DH_REQUIRE(n <= h->max_chunk, DH_E_INVALID, "dh_pipe_process_device: n=%zu exceeds max_chunk=%zu", n, h->max_chunk);
+    if (n == 0) return DH_OK;
+    cudaStream_t user = (cudaStream_t) stream;
+    dh::DeviceGuard guard(h->device);
+    if (!h->rrc || h->sub_chunk == 0 || n <= h->sub_chunk) return run_stages(h, d_in, in_pitch, n, user, user, nullptr, nullptr);
+
+    // pipelined: K1(c) on stream a; K2(c) + decoder(c) on stream b after K1(c); K1(c) may only overwrite the
+    // demodulator rows it alternates into once K2(c - 2), their previous reader, is done
+    const size_t sub = h->sub_chunk;
+    const size_t nsub = (n + sub - 1) / sub;
+    while (h->ev_k1.size() < nsub) {
+        cudaEvent_t a, b;
+        DH_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        DH_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_k1.push_back(a);
+        h->ev_k2.push_back(b);
+    }
+    DH_CUDA(cudaEventRecord(h->ev_start, user));
+    DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_start, 0));
+    DH_CUDA(cudaStreamWaitEvent(h->sb, h->ev_start, 0));
+    for (size_t c = 0; c < nsub; c++) {
+        const size_t off = c * sub;
+        const size_t len = n - off < sub ? n - off : sub;
+        if (c >= 2) DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_k2[c - 2], 0));
+        int rc = run_stages(h, d_in + off, in_pitch, len, h->sa, h->sb, h->ev_k1[c], h->ev_k2[c]);
+        if (rc != DH_OK) return rc;
+    }
+    // everything on stream a precedes the last K2 on stream b
+    DH_CUDA(cudaEventRecord(h->ev_done, h->sb));
+    DH_CUDA(cudaStreamWaitEvent(user, h->ev_done, 0));
+    return DH_OK;
+}
+
+int dh_pipe_set_sub_chunk(dh_pipe* h, size_t sub_chunk) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_set_sub_chunk: handle is NULL");
+    DH_REQUIRE(sub_chunk % 4 == 0, DH_E_INVALID, "dh_pipe_set_sub_chunk: must be a multiple of 4");
+    h->sub_chunk = sub_chunk;
+    return DH_OK;
 }
 
 int dh_pipe_set_profiling(dh_pipe* h, int enable) {
@@ -123,12 +188,12 @@ int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_stage_times: handle is NULL");
     dh::DeviceGuard guard(h->device);
     double acc[3] = {0, 0, 0};
-    const size_t ncalls = h->events.size() / 4;
+    const size_t ncalls = h->events.size() / 6;
     for (size_t c = 0; c < ncalls; c++) {
-        DH_CUDA(cudaEventSynchronize(h->events[4 * c + 3]));
         for (int k = 0; k < 3; k++) {
             float t = 0;
-            DH_CUDA(cudaEventElapsedTime(&t, h->events[4 * c + k], h->events[4 * c + k + 1]));
+            DH_CUDA(cudaEventSynchronize(h->events[6 * c + 2 * k + 1]));
+            DH_CUDA(cudaEventElapsedTime(&t, h->events[6 * c + 2 * k], h->events[6 * c + 2 * k + 1]));
             acc[k] += t;
         }
     }
@@ -196,7 +261,16 @@ size_t dh_pipe_host_pitch(const dh_pipe* h) { return h ? (h->max_chunk + 3) & ~(
 
 void dh_pipe_destroy(dh_pipe* h) {
     if (!h) return;
-    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+    {
+        dh::DeviceGuard guard(h->device);
+        for (cudaEvent_t e : h->events) cudaEventDestroy(e);
+        for (cudaEvent_t e : h->ev_k1) cudaEventDestroy(e);
+        for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
+        if (h->ev_start) cudaEventDestroy(h->ev_start);
+        if (h->ev_done) cudaEventDestroy(h->ev_done);
+        if (h->sa) cudaStreamDestroy(h->sa);
+        if (h->sb) cudaStreamDestroy(h->sb);
+    }
     dh_rrc_destroy(h->rrc);
     dh_demod_destroy(h->demod);
     dh_decoder_destroy(h->decoder);

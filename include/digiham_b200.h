@@ -212,9 +212,16 @@ DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
 DH_API dh_decoder* dh_pipe_decoder(dh_pipe* h);
 /* device views of the symbols the demodulator produced in the LAST process call (parity artefact) */
 DH_API int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, const uint32_t** d_nsym);
+/* Software pipelining inside one process call: the chunk is cut into sub-chunks of `sub_chunk` samples (multiple
+ * of 4) and K1 of sub-chunk c+1 runs concurrently with K2 + decoder of sub-chunk c on two internal streams; the
+ * caller's stream is joined before the call returns control of it.  0 (the default) runs the three kernels back to
+ * back on the caller's stream.  Results are identical either way. */
+DH_API int dh_pipe_set_sub_chunk(dh_pipe* h, size_t sub_chunk);
 /* Per-stage device timing: when enabled every process call records CUDA events on the caller's stream around
- * K1 (RRC), K2 (demodulator) and the decoder kernel.  dh_pipe_stage_times waits for the recorded work, returns
- * the summed milliseconds per stage since the previous query and the number of calls they cover. */
+ * K1 (RRC), K2 (demodulator) and the decoder kernel, each on the stream the kernel runs on.
+ * dh_pipe_stage_times waits for the recorded work, returns the summed milliseconds per stage since the previous
+ * query and the number of (sub-)chunks they cover.  With pipelining the stages overlap, so the three sums can
+ * exceed the wall time of the call. */
 DH_API int dh_pipe_set_profiling(dh_pipe* h, int enable);
 DH_API int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls);
 /* kernels launched by this pipe since creation */

@@ -17,12 +17,17 @@ from digiham_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _run_pipe(x, chunk, host=False, want_symbols=False):
-    """x: float32 torch tensor [C, pitch] (cuda); returns per-channel (symbols, bytes, meta)."""
+def _run_pipe(x, chunk, host=False, want_symbols=False, sub_chunk=None):
+    """x: float32 torch tensor [C, pitch] (cuda); returns per-channel (symbols, bytes, meta).
+    sub_chunk: software-pipelining granularity (None = library default, 0 = off)."""
     import digiham_b200 as dh
     C = x.shape[0]
     n = x.shape[1]
     pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=chunk)
+    if want_symbols:
+        sub_chunk = 0        # last_symbols() only sees the final sub-chunk of a pipelined call
+    if sub_chunk is not None:
+        pipe.set_sub_chunk(sub_chunk)
     syms = [[] for _ in range(C)]
     for pos in range(0, n, chunk):
         c = min(chunk, n - pos)
@@ -57,6 +62,11 @@ def test_pipe_dmr_vs_oracle():
         assert got[ch][2] == metas[ch], "channel %d meta differs" % ch
         voice += len(got[ch][1])
     assert voice > 27 * 200, "workload did not produce voice frames"
+    # the software-pipelined schedule (sub-chunks on two streams) must not change a single byte
+    for sub in (None, 4352, 1000):
+        piped = _run_pipe(x[:, :n], chunk=24000, sub_chunk=sub)
+        for ch in range(C):
+            assert piped[ch][1] == got[ch][1] and piped[ch][2] == got[ch][2], (sub, ch)
 
 
 def test_pipe_host_input_equals_device_input():
