@@ -79,6 +79,57 @@ def main():
     g["bptc_in"] = pay
     g["bptc_out"] = np.stack([np.concatenate([[int(ref.bptc(p)[0])], ref.bptc(p)[1]]) for p in pay]).astype(np.uint8)
 
+    # YSF decoder (all modes, symbol errors) and POCSAG decoder on bit streams; whole pipes on samples
+    for k, (mode, err) in enumerate([("DN", 0.0), ("mix", 0.01), ("VW", 0.003)]):
+        sym = synth.ysf_symbols(14, seed=200 + k, mode=mode, symbol_errors=err)
+        o, m = ref.decode(oracle_lib.PROTO_YSF, sym)
+        g["ysf%d_sym" % k] = sym
+        g["ysf%d_out" % k] = o
+        g["ysf%d_meta" % k] = np.frombuffer(m, dtype=np.uint8)
+    bits = synth.pocsag_bits([(1234562, 3, "HELLO B200"), (77, 3, "THE QUICK BROWN FOX"), (9000, 1, "x"), (8, 3, "A")],
+                             seed=1, bit_errors=2, lead_in=40)
+    g["pocsag_bits"] = bits
+    g["pocsag_out"] = ref.decode(oracle_lib.PROTO_POCSAG, bits)[0]
+    xp = synth.modulate(bits[:1300], sps=40, levels=synth.LEVELS2[::-1].copy(), snr_db=15, ppm=200,
+                        rng=np.random.default_rng(2))
+    g["pocsag_pipe_in"] = xp
+    ps, po, _ = ref.pipe(oracle_lib.PROTO_POCSAG, xp)
+    g["pocsag_pipe_sym"] = ps
+    g["pocsag_pipe_out"] = po
+    ys = synth.ysf_symbols(6, seed=300, mode="DN", lead_in=30)
+    xy = synth.modulate(ys, sps=10, snr_db=16, phase=5, rng=np.random.default_rng(3))
+    g["ysf_pipe_in"] = xy
+    _, yo, ym = ref.pipe(oracle_lib.PROTO_YSF, xy)
+    g["ysf_pipe_out"] = yo
+    g["ysf_pipe_meta"] = np.frombuffer(ym, dtype=np.uint8)
+
+    # K6 and the YSF primitives
+    a = rng.integers(-32768, 32768, 1500).astype(np.int16)
+    a[:200] = (15000 * np.sin(np.arange(200) * 0.3)).astype(np.int16)
+    g["dvf_in"] = a
+    g["dvf_out"] = ref.dvf(a)
+    for steps in (100, 180):
+        packed = rng.integers(0, 256, size=(6, (steps + 3) // 4)).astype(np.uint8)
+        # first rows: valid code sequences with a few dibit errors
+        for r in range(3):
+            enc = synth.ysf_conv_encode(rng.integers(0, 2, steps)).copy()
+            for e in rng.choice(steps, size=r * 2, replace=False):
+                enc[e] ^= int(rng.integers(1, 4))
+            pk = np.zeros((steps + 3) // 4, dtype=np.uint8)
+            for i in range(steps):
+                pk[i // 4] |= enc[i] << (6 - 2 * (i % 4))
+            packed[r] = pk
+        res = []
+        for r in range(6):
+            metric, bits_out = ref.trellis(packed[r], steps)
+            res.append(np.concatenate([[metric], bits_out]))
+        g["trellis%d_in" % steps] = packed
+        g["trellis%d_out" % steps] = np.stack(res).astype(np.uint8)
+    blob = rng.integers(0, 256, 40).astype(np.uint8)
+    g["crc_in"] = blob
+    g["crc_out"] = np.array([ref.crc16(blob[:k]) for k in (4, 10, 20, 40)], dtype=np.uint32)
+    g["whitening_out"] = ref.whitening(blob[:20], 160)
+
     path = os.path.join(HERE, "golden_v1.npz")
     np.savez_compressed(path, **g)
     print("wrote", path, os.path.getsize(path), "bytes,", len(g), "arrays")

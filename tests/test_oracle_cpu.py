@@ -88,6 +88,35 @@ def test_block_codes_golden(orc):
     assert GOLDEN["bptc_out"][:10, 0].all(), "valid BPTC blocks with <= 4 bit errors must decode"
 
 
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_ysf_pocsag_dvf_golden(orc):
+    for k in range(3):
+        out, meta = orc.decode(oracle_lib.PROTO_YSF, GOLDEN["ysf%d_sym" % k])
+        assert np.array_equal(out, GOLDEN["ysf%d_out" % k]), k
+        assert meta == GOLDEN["ysf%d_meta" % k].tobytes(), k
+    assert b"mode:DN" in GOLDEN["ysf0_meta"].tobytes() and b"lat:" in GOLDEN["ysf0_meta"].tobytes()
+    out, _ = orc.decode(oracle_lib.PROTO_POCSAG, GOLDEN["pocsag_bits"])
+    assert np.array_equal(out, GOLDEN["pocsag_out"]) and b"message:THE QUICK BROWN FOX" in out.tobytes()
+    sym, out, _ = orc.pipe(oracle_lib.PROTO_POCSAG, GOLDEN["pocsag_pipe_in"])
+    assert np.array_equal(sym, GOLDEN["pocsag_pipe_sym"]) and np.array_equal(out, GOLDEN["pocsag_pipe_out"])
+    _, out, meta = orc.pipe(oracle_lib.PROTO_YSF, GOLDEN["ysf_pipe_in"])
+    assert np.array_equal(out, GOLDEN["ysf_pipe_out"]) and meta == GOLDEN["ysf_pipe_meta"].tobytes()
+    assert np.array_equal(orc.dvf(GOLDEN["dvf_in"]), GOLDEN["dvf_out"])
+    assert np.array_equal(orc.dvf(GOLDEN["dvf_in"], chunk=77), GOLDEN["dvf_out"])
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_ysf_primitives_golden(orc):
+    for steps in (100, 180):
+        for packed, exp in zip(GOLDEN["trellis%d_in" % steps], GOLDEN["trellis%d_out" % steps]):
+            metric, bits = orc.trellis(packed, steps)
+            assert metric == exp[0] and np.array_equal(bits, exp[1:])
+        assert GOLDEN["trellis%d_out" % steps][0, 0] == 0      # an error-free code sequence decodes with metric 0
+    blob = GOLDEN["crc_in"]
+    assert [orc.crc16(blob[:k]) for k in (4, 10, 20, 40)] == [int(v) for v in GOLDEN["crc_out"]]
+    assert np.array_equal(orc.whitening(blob[:20], 160), GOLDEN["whitening_out"])
+
+
 def test_generated_luts_match_reference_for_every_syndrome():
     """tools/gen_tables.py derives H and the correction LUTs from the published generator matrices; the result
     must equal what the reference's linear search over corrections[] does (golden = compiled reference)."""
@@ -123,3 +152,19 @@ def test_port_equals_reference_on_random_streams():
         a = ref.pipe(oracle_lib.PROTO_DMR, xb[c, :40000].numpy())
         b = port.pipe(oracle_lib.PROTO_DMR, xb[c, :40000].numpy())
         assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    for k, mode in enumerate(["DN", "V1", "VW", "mix", "FR"]):
+        sym = synth.ysf_symbols(25, seed=50 + k, mode=mode, symbol_errors=[0.0, 0.01, 0.04][k % 3])
+        a = ref.decode(oracle_lib.PROTO_YSF, sym)
+        b = port.decode(oracle_lib.PROTO_YSF, sym)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], mode
+    for k in range(4):
+        bits = synth.pocsag_bits([(100 + k, 3, "PORT VS REFERENCE %d" % k), (5, 1, ""), (77777, 3, "x" * 70)],
+                                 seed=k, bit_errors=k, lead_in=17 * k)
+        assert np.array_equal(ref.decode(oracle_lib.PROTO_POCSAG, bits)[0], port.decode(oracle_lib.PROTO_POCSAG, bits)[0])
+    a16 = rng.integers(-32768, 32768, 6000).astype(np.int16)
+    assert np.array_equal(ref.dvf(a16), port.dvf(a16))
+    for sps, four, inv in ((10, True, False), (20, True, False), (40, False, True), (7, False, False)):
+        sig = synth.modulate(synth.random_symbols(700, 4 if four else 2, seed=sps),
+                             sps=sps, levels=synth.LEVELS4 if four else synth.LEVELS2, ppm=500, snr_db=12,
+                             rng=np.random.default_rng(sps))
+        assert np.array_equal(ref.demod(sig, sps, four, inv), port.demod(sig, sps, four, inv)), sps
