@@ -84,6 +84,10 @@ def lib():
     L.dh_pipe_last_symbols.argtypes = [ctypes.c_void_p, c_void_pp, ctypes.POINTER(ctypes.c_size_t), c_void_pp]
     L.dh_pipe_read_symbols.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_size_t,
                                        ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_pipe_submit_host.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t]
+    L.dh_pipe_collect_step.argtypes = [ctypes.c_void_p]
+    L.dh_decoder_select_results.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dh_decoder_collect_results.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.dh_pipe_set_sub_chunk.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.dh_pipe_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.dh_pipe_stage_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
@@ -334,6 +338,17 @@ class Pipe:
 
     def collect(self, stream=None):
         check(lib().dh_pipe_collect(self._h, _stream_ptr(stream)))
+
+    def submit(self, x, n=None):
+        """Streaming interface: asynchronous upload + kernels of one block from PINNED host memory."""
+        assert (not x.is_cuda) and x.is_pinned() and x.dtype == torch.float32 and x.shape[0] == self.channels
+        if n is None:
+            n = x.shape[1]
+        check(lib().dh_pipe_submit_host(self._h, x.data_ptr(), x.stride(0), n))
+
+    def collect_step(self):
+        """Waits for the oldest submitted step and appends its results to the per-channel host buffers."""
+        check(lib().dh_pipe_collect_step(self._h))
 
     def set_sub_chunk(self, sub_chunk):
         """Software pipelining granularity inside one process call (0 = three kernels back to back)."""

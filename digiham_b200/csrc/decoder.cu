@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <thread>
 #include <vector>
 
 using dh::DecEvent;
@@ -26,11 +27,13 @@ struct dh_decoder {
     uint8_t* d_sym = nullptr;
     size_t sym_pitch = 0;
     size_t max_syms = 0;
-    uint8_t* d_out = nullptr;
+    // two result sets so that a streaming caller can read the results of step k while step k+1 is being decoded
+    uint8_t* d_out_set[2] = {nullptr, nullptr};
     uint32_t out_cap = 0;
-    DecEvent* d_ev = nullptr;
+    DecEvent* d_ev_set[2] = {nullptr, nullptr};
     uint32_t ev_cap = 0;
-    uint32_t* d_counts = nullptr;      // [3][channels]: out_len, ev_len, flags
+    uint32_t* d_counts_set[2] = {nullptr, nullptr};   // each [3][channels]: out_len, ev_len, flags
+    int active = 0;                    // set written by dh_decoder_process
     uint8_t* d_slot_filter = nullptr;
     std::vector<uint8_t> h_slot_filter;
     bool filter_dirty = true;
@@ -51,7 +54,7 @@ struct dh_decoder {
 
 namespace {
 
-int decoder_collect(dh_decoder* h, cudaStream_t st);
+int decoder_collect(dh_decoder* h, int set, cudaStream_t st);
 
 int decoder_reserve(dh_decoder* h, size_t max_syms) {
     if (h->d_sym && max_syms <= h->max_syms) return DH_OK;
@@ -60,8 +63,10 @@ int decoder_reserve(dh_decoder* h, size_t max_syms) {
     if (h->d_sym) {
         // mid-stream growth: drain pending results, keep the carried symbol tails
         DH_CUDA(cudaDeviceSynchronize());
-        int rc = decoder_collect(h, nullptr);
-        if (rc != DH_OK) return rc;
+        for (int set = 0; set < 2; set++) {
+            int rc = decoder_collect(h, set, nullptr);
+            if (rc != DH_OK) return rc;
+        }
     }
     uint8_t* ns = nullptr;
     DH_CUDA(cudaMalloc(&ns, (size_t) h->channels * pitch));
@@ -70,18 +75,22 @@ int decoder_reserve(dh_decoder* h, size_t max_syms) {
         DH_CUDA(cudaMemcpy2D(ns, pitch, h->d_sym, h->sym_pitch, (size_t) h->ops->carry_cap, h->channels,
                              cudaMemcpyDeviceToDevice));
         DH_CUDA(cudaFree(h->d_sym));
-        DH_CUDA(cudaFree(h->d_out));
-        DH_CUDA(cudaFree(h->d_ev));
-        h->d_out = nullptr;
-        h->d_ev = nullptr;
+        for (int set = 0; set < 2; set++) {
+            DH_CUDA(cudaFree(h->d_out_set[set]));
+            DH_CUDA(cudaFree(h->d_ev_set[set]));
+            h->d_out_set[set] = nullptr;
+            h->d_ev_set[set] = nullptr;
+        }
     }
     h->d_sym = ns;
     h->sym_pitch = pitch;
     h->max_syms = m16;
     h->out_cap = (h->ops->out_bytes(m16) * kAccumulate + 15u) & ~15u;
     h->ev_cap = h->ops->events(m16) * kAccumulate;
-    DH_CUDA(cudaMalloc(&h->d_out, (size_t) h->channels * h->out_cap));
-    DH_CUDA(cudaMalloc(&h->d_ev, (size_t) h->channels * h->ev_cap * sizeof(DecEvent)));
+    for (int set = 0; set < 2; set++) {
+        DH_CUDA(cudaMalloc(&h->d_out_set[set], (size_t) h->channels * h->out_cap));
+        DH_CUDA(cudaMalloc(&h->d_ev_set[set], (size_t) h->channels * h->ev_cap * sizeof(DecEvent)));
+    }
     return DH_OK;
 }
 
@@ -96,10 +105,13 @@ int grow_pinned(void** p, size_t* have, size_t need) {
     return DH_OK;
 }
 
-int decoder_collect(dh_decoder* h, cudaStream_t st) {
-    if (!h->d_out) return DH_OK;
+int decoder_collect(dh_decoder* h, int set, cudaStream_t st) {
+    if (!h->d_out_set[set]) return DH_OK;
     const uint32_t n = h->channels;
-    DH_CUDA(cudaMemcpyAsync(h->h_counts, h->d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint8_t* d_out = h->d_out_set[set];
+    DecEvent* d_ev = h->d_ev_set[set];
+    uint32_t* d_counts = h->d_counts_set[set];
+    DH_CUDA(cudaMemcpyAsync(h->h_counts, d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
     DH_CUDA(cudaStreamSynchronize(st));
     h->total_d2h += 3 * (uint64_t) n * sizeof(uint32_t);
     const uint32_t* out_len = h->h_counts;
@@ -114,32 +126,54 @@ int decoder_collect(dh_decoder* h, cudaStream_t st) {
     if (max_out) {
         int rc = grow_pinned((void**) &h->h_out, &h->h_out_bytes, (size_t) n * max_out);
         if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->h_out, max_out, h->d_out, h->out_cap, max_out, n, cudaMemcpyDeviceToHost, st));
+        DH_CUDA(cudaMemcpy2DAsync(h->h_out, max_out, d_out, h->out_cap, max_out, n, cudaMemcpyDeviceToHost, st));
         h->total_d2h += (uint64_t) n * max_out;
     }
     if (max_ev) {
         const size_t w = (size_t) max_ev * sizeof(DecEvent);
         int rc = grow_pinned((void**) &h->h_ev, &h->h_ev_bytes, (size_t) n * w);
         if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->h_ev, w, h->d_ev, (size_t) h->ev_cap * sizeof(DecEvent), w, n,
+        DH_CUDA(cudaMemcpy2DAsync(h->h_ev, w, d_ev, (size_t) h->ev_cap * sizeof(DecEvent), w, n,
                                   cudaMemcpyDeviceToHost, st));
         h->total_d2h += (uint64_t) n * w;
     }
-    DH_CUDA(cudaMemsetAsync(h->d_counts, 0, 3 * (size_t) n * sizeof(uint32_t), st));
+    DH_CUDA(cudaMemsetAsync(d_counts, 0, 3 * (size_t) n * sizeof(uint32_t), st));
     DH_CUDA(cudaStreamSynchronize(st));
-    for (uint32_t c = 0; c < n; c++) {
-        dh::ChannelResult& r = h->results[c];
-        if (out_len[c]) {
-            r.bytes.append(reinterpret_cast<const char*>(h->h_out + (size_t) c * max_out), out_len[c]);
-            h->total_bytes += out_len[c];
+    // per-channel appends and metadata replay are independent: spread them over a few host threads
+    auto work = [&](uint32_t c0, uint32_t c1, uint64_t* sums) {
+        for (uint32_t c = c0; c < c1; c++) {
+            dh::ChannelResult& r = h->results[c];
+            if (out_len[c]) {
+                r.bytes.append(reinterpret_cast<const char*>(h->h_out + (size_t) c * max_out), out_len[c]);
+                sums[0] += out_len[c];
+            }
+            sums[2] += ev_len[c];
+            if (ev_len[c] && h->replay[c]) {
+                const size_t before = r.meta.size();
+                h->replay[c]->kv_sink = &r.meta_kv;
+                h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
+                sums[1] += r.meta.size() - before;
+            }
         }
-        h->total_events += ev_len[c];
-        if (ev_len[c] && h->replay[c]) {
-            const size_t before = r.meta.size();
-            h->replay[c]->kv_sink = &r.meta_kv;
-            h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
-            h->total_meta += r.meta.size() - before;
+    };
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
+    if (n < 256) nthreads = 1;
+    std::vector<uint64_t> sums((size_t) nthreads * 8, 0);   // 8 slots apart: no false sharing
+    if (nthreads == 1) {
+        work(0, n, sums.data());
+    } else {
+        std::vector<std::thread> pool;
+        const uint32_t per = (n + nthreads - 1) / nthreads;
+        for (unsigned t = 0; t < nthreads; t++) {
+            const uint32_t c0 = std::min(n, t * per), c1 = std::min(n, (t + 1) * per);
+            pool.emplace_back(work, c0, c1, sums.data() + (size_t) t * 8);
         }
+        for (auto& t : pool) t.join();
+    }
+    for (unsigned t = 0; t < nthreads; t++) {
+        h->total_bytes += sums[(size_t) t * 8];
+        h->total_meta += sums[(size_t) t * 8 + 1];
+        h->total_events += sums[(size_t) t * 8 + 2];
     }
     DH_REQUIRE(any_flags == 0, DH_E_STATE,
                "dh_decoder_collect: device result buffers overflowed (flags 0x%x): collect after every %u process calls",
@@ -187,8 +221,10 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
     ops->init_states(init.data(), channels);
     cudaError_t e = cudaMalloc(&h->d_states, init.size());
     if (e == cudaSuccess) e = cudaMemcpy(h->d_states, init.data(), init.size(), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess) e = cudaMalloc(&h->d_counts, 3 * (size_t) channels * sizeof(uint32_t));
-    if (e == cudaSuccess) e = cudaMemset(h->d_counts, 0, 3 * (size_t) channels * sizeof(uint32_t));
+    for (int set = 0; set < 2; set++) {
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_counts_set[set], 3 * (size_t) channels * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMemset(h->d_counts_set[set], 0, 3 * (size_t) channels * sizeof(uint32_t));
+    }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_slot_filter, channels);
     if (e == cudaSuccess) e = cudaHostAlloc((void**) &h->h_counts, 3 * (size_t) channels * sizeof(uint32_t),
                                             cudaHostAllocDefault);
@@ -246,11 +282,11 @@ int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, co
     io.sym = h->d_sym;
     io.sym_pitch = h->sym_pitch;
     io.nsym = d_nsym;
-    io.out = h->d_out;
-    io.out_len = h->d_counts;
-    io.ev = h->d_ev;
-    io.ev_len = h->d_counts + h->channels;
-    io.flags = h->d_counts + 2 * (size_t) h->channels;
+    io.out = h->d_out_set[h->active];
+    io.out_len = h->d_counts_set[h->active];
+    io.ev = h->d_ev_set[h->active];
+    io.ev_len = h->d_counts_set[h->active] + h->channels;
+    io.flags = h->d_counts_set[h->active] + 2 * (size_t) h->channels;
     io.out_cap = h->out_cap;
     io.ev_cap = h->ev_cap;
     io.carry_cap = h->ops->carry_cap;
@@ -261,7 +297,19 @@ int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, co
 int dh_decoder_collect(dh_decoder* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_collect: handle is NULL");
     dh::DeviceGuard guard(h->device);
-    return decoder_collect(h, (cudaStream_t) stream);
+    return decoder_collect(h, h->active, (cudaStream_t) stream);
+}
+
+int dh_decoder_select_results(dh_decoder* h, int set) {
+    DH_REQUIRE(h != nullptr && (set == 0 || set == 1), DH_E_INVALID, "dh_decoder_select_results: bad argument");
+    h->active = set;
+    return DH_OK;
+}
+
+int dh_decoder_collect_results(dh_decoder* h, int set, void* stream) {
+    DH_REQUIRE(h != nullptr && (set == 0 || set == 1), DH_E_INVALID, "dh_decoder_collect_results: bad argument");
+    dh::DeviceGuard guard(h->device);
+    return decoder_collect(h, set, (cudaStream_t) stream);
 }
 
 int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len) {
@@ -301,9 +349,10 @@ int dh_decoder_stats(dh_decoder* h, uint64_t* events, uint64_t* d2h_bytes) {
 
 int dh_decoder_discard(dh_decoder* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_discard: handle is NULL");
-    if (!h->d_counts) return DH_OK;
+    if (!h->d_counts_set[h->active]) return DH_OK;
     dh::DeviceGuard guard(h->device);
-    DH_CUDA(cudaMemsetAsync(h->d_counts, 0, 3 * (size_t) h->channels * sizeof(uint32_t), (cudaStream_t) stream));
+    DH_CUDA(cudaMemsetAsync(h->d_counts_set[h->active], 0, 3 * (size_t) h->channels * sizeof(uint32_t),
+                            (cudaStream_t) stream));
     return DH_OK;
 }
 
@@ -339,9 +388,11 @@ void dh_decoder_destroy(dh_decoder* h) {
     dh::DeviceGuard guard(h->device);
     cudaFree(h->d_states);
     cudaFree(h->d_sym);
-    cudaFree(h->d_out);
-    cudaFree(h->d_ev);
-    cudaFree(h->d_counts);
+    for (int set = 0; set < 2; set++) {
+        cudaFree(h->d_out_set[set]);
+        cudaFree(h->d_ev_set[set]);
+        cudaFree(h->d_counts_set[set]);
+    }
     cudaFree(h->d_slot_filter);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_out) cudaFreeHost(h->h_out);

@@ -26,8 +26,17 @@ struct dh_pipe {
     size_t sym_pitch = 0;
     size_t max_syms = 0;
     uint32_t* d_nsym = nullptr;
-    float* d_stage = nullptr;     // device staging for host input
+    float* d_stage = nullptr;     // device staging for host input (dh_pipe_process_host)
     size_t stage_pitch = 0;
+    // streaming host interface (dh_pipe_submit_host / dh_pipe_collect_step): two steps in flight, the upload of
+    // step k+1 (copy stream) overlaps kernels + result read-back + metadata replay of step k
+    float* d_slot[2] = {nullptr, nullptr};
+    cudaStream_t s_copy = nullptr, s_compute = nullptr, s_back = nullptr;
+    cudaStream_t s_copy_back() const { return s_back; }
+    cudaEvent_t ev_uploaded[2] = {nullptr, nullptr};   // H2D of the slot finished
+    cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // K1 finished reading the slot
+    cudaEvent_t ev_decoded[2] = {nullptr, nullptr};    // decoder kernel of the step finished
+    uint64_t submitted = 0, collected = 0;
     // optional per-stage device timing: CUDA events around every kernel, on the stream it is launched on
     bool profiling = false;
     std::vector<cudaEvent_t> events;   // groups of 6: K1 start/end, K2 start/end, decoder start/end
@@ -229,6 +238,67 @@ int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t 
     return dh_pipe_process_device(h, h->d_stage, h->stage_pitch, n, stream);
 }
 
+int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_submit_host: handle is NULL");
+    DH_REQUIRE(n > 0 && n <= h->max_chunk, DH_E_INVALID, "dh_pipe_submit_host: n=%zu out of range (max_chunk=%zu)", n,
+               h->max_chunk);
+    DH_REQUIRE(h_in != nullptr && in_pitch >= n, DH_E_INVALID, "dh_pipe_submit_host: bad input buffer");
+    DH_REQUIRE(h->submitted - h->collected < 2, DH_E_STATE,
+               "dh_pipe_submit_host: two steps are already in flight, call dh_pipe_collect_step first");
+    dh::DeviceGuard guard(h->device);
+    const int slot = (int) (h->submitted & 1);
+    if (!h->s_copy) {
+        h->stage_pitch = (h->max_chunk + 3) & ~(size_t) 3;
+        DH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+        DH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
+        DH_CUDA(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            DH_CUDA(cudaMalloc(&h->d_slot[i], (size_t) h->channels * h->stage_pitch * sizeof(float)));
+            DH_CUDA(cudaMemset(h->d_slot[i], 0, (size_t) h->channels * h->stage_pitch * sizeof(float)));
+            DH_CUDA(cudaEventCreateWithFlags(&h->ev_uploaded[i], cudaEventDisableTiming));
+            DH_CUDA(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
+            DH_CUDA(cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming));
+        }
+    }
+    // upload into the slot once K1 of the step that used it two submissions ago has read it
+    if (h->submitted >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_consumed[slot], 0));
+    if (in_pitch == h->stage_pitch) {
+        DH_CUDA(cudaMemcpyAsync(h->d_slot[slot], h_in, (size_t) h->channels * in_pitch * sizeof(float),
+                                cudaMemcpyHostToDevice, h->s_copy));
+    } else {
+        DH_CUDA(cudaMemcpy2DAsync(h->d_slot[slot], h->stage_pitch * sizeof(float), h_in, in_pitch * sizeof(float),
+                                  n * sizeof(float), h->channels, cudaMemcpyHostToDevice, h->s_copy));
+    }
+    DH_CUDA(cudaEventRecord(h->ev_uploaded[slot], h->s_copy));
+    DH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_uploaded[slot], 0));
+    // results of this step go to the result set of its parity
+    int rc = dh_decoder_select_results(h->decoder, slot);
+    if (rc != DH_OK) return rc;
+    const size_t saved_sub = h->sub_chunk;
+    h->sub_chunk = 0;
+    rc = run_stages(h, h->d_slot[slot], h->stage_pitch, n, h->s_compute, h->s_compute, nullptr, nullptr);
+    h->sub_chunk = saved_sub;
+    if (rc != DH_OK) return rc;
+    // K1 is the only reader of the slot, but the stages are serialised on one stream anyway
+    DH_CUDA(cudaEventRecord(h->ev_consumed[slot], h->s_compute));
+    DH_CUDA(cudaEventRecord(h->ev_decoded[slot], h->s_compute));
+    h->submitted++;
+    return DH_OK;
+}
+
+int dh_pipe_collect_step(dh_pipe* h) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_collect_step: handle is NULL");
+    DH_REQUIRE(h->collected < h->submitted, DH_E_STATE, "dh_pipe_collect_step: nothing in flight");
+    dh::DeviceGuard guard(h->device);
+    const int slot = (int) (h->collected & 1);
+    DH_CUDA(cudaEventSynchronize(h->ev_decoded[slot]));
+    // read-back on the copy-independent compute-side helper: the default stream would serialise with everything
+    int rc = dh_decoder_collect_results(h->decoder, slot, h->s_copy_back());
+    if (rc != DH_OK) return rc;
+    h->collected++;
+    return DH_OK;
+}
+
 int dh_pipe_collect(dh_pipe* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_collect: handle is NULL");
     return dh_decoder_collect(h->decoder, stream);
@@ -270,6 +340,15 @@ void dh_pipe_destroy(dh_pipe* h) {
         if (h->ev_done) cudaEventDestroy(h->ev_done);
         if (h->sa) cudaStreamDestroy(h->sa);
         if (h->sb) cudaStreamDestroy(h->sb);
+        if (h->s_copy) cudaStreamDestroy(h->s_copy);
+        if (h->s_compute) cudaStreamDestroy(h->s_compute);
+        if (h->s_back) cudaStreamDestroy(h->s_back);
+        for (int i = 0; i < 2; i++) {
+            if (h->ev_uploaded[i]) cudaEventDestroy(h->ev_uploaded[i]);
+            if (h->ev_consumed[i]) cudaEventDestroy(h->ev_consumed[i]);
+            if (h->ev_decoded[i]) cudaEventDestroy(h->ev_decoded[i]);
+            cudaFree(h->d_slot[i]);
+        }
     }
     dh_rrc_destroy(h->rrc);
     dh_demod_destroy(h->demod);

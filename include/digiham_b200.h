@@ -165,6 +165,12 @@ DH_API int dh_decoder_process_host(dh_decoder* h, uint32_t channels, const uint8
 /* Synchronises with `stream`, copies everything produced since the last collect to the host and appends it to
  * the per-channel host buffers.  Must be called at least once every 2 process calls. */
 DH_API int dh_decoder_collect(dh_decoder* h, void* stream);
+/* Two device result sets exist so that a streaming caller can read step k while step k+1 is decoded:
+ * dh_decoder_select_results chooses the set the next process calls append to (default 0, which is also what
+ * dh_decoder_collect / dh_decoder_discard act on: they use the selected set); dh_decoder_collect_results collects a
+ * given set. */
+DH_API int dh_decoder_select_results(dh_decoder* h, int set);
+DH_API int dh_decoder_collect_results(dh_decoder* h, int set, void* stream);
 /* Host views of one channel's accumulated results; valid until the next collect / clear / destroy. */
 DH_API int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len);
 DH_API int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len);
@@ -206,6 +212,14 @@ DH_API int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch
  * is part of the call.  A pitch of dh_pipe_host_pitch() allows one contiguous transfer. */
 DH_API int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream);
 DH_API size_t dh_pipe_host_pitch(const dh_pipe* h);
+/* Streaming host interface: up to two steps in flight.  dh_pipe_submit_host starts the asynchronous upload of a
+ * block from PINNED host memory (which must stay untouched until the step is collected) followed by the three
+ * kernels on internal streams and returns at once; dh_pipe_collect_step waits for the OLDEST step in flight, reads
+ * its frames / metadata back and appends them to the per-channel host buffers.  The upload of step k+1 overlaps
+ * kernels, read-back and metadata replay of step k.  Do not mix with dh_pipe_process_* on the same pipe while steps
+ * are in flight.  DH_E_STATE when two steps are already in flight / nothing is in flight. */
+DH_API int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n);
+DH_API int dh_pipe_collect_step(dh_pipe* h);
 /* same contract as dh_decoder_collect */
 DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
 /* the decoder bank of the pipe: use dh_decoder_output / _meta / _totals / _clear / _set_slot_filter on it */
