@@ -112,8 +112,11 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
         w[r] = sw[r];
     }
 
+    // a ragged last tile: warps whose outputs all lie beyond the end of the stream skip the arithmetic
+    // (warp-uniform, so no divergence inside the FMUL/FADD stream)
+    const bool warp_live = (tid & ~31) * kR < valid;
     const int ntaps = nz + 1;
-    const int full = ntaps / kR;
+    const int full = warp_live ? ntaps / kR : 0;
     int i0 = 0;
 #pragma unroll 1
     for (int it = 0; it < full; it++, i0 += kR) {
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
             if (i0 + k < nz) w[k] = nxt[k];
         }
     }
-    {
+    if (warp_live) {
         const int rem = ntaps - i0;   // < kR, identical for all threads
         const float* nxt = sw + i0 + kR;
 #pragma unroll
