@@ -20,8 +20,10 @@ from ._capi import (  # noqa: F401
     PROTO_DMR,
     PROTO_YSF,
     PROTO_POCSAG,
+    PROTO_NXDN,
+    PROTO_DSTAR,
     RRC_WIDE,
     RRC_NARROW,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "RRC_WIDE", "RRC_NARROW"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "PROTO_NXDN", "PROTO_DSTAR", "RRC_WIDE", "RRC_NARROW"]

@@ -9,7 +9,7 @@ _LIB_NAME = "libdigiham_b200.so"
 
 RRC_WIDE = 0
 RRC_NARROW = 1
-PROTO_DMR, PROTO_YSF, PROTO_POCSAG = 0, 1, 2
+PROTO_DMR, PROTO_YSF, PROTO_POCSAG, PROTO_NXDN, PROTO_DSTAR = 0, 1, 2, 3, 4
 
 
 class DhError(RuntimeError):

@@ -21,5 +21,6 @@ struct ProtoOps {
 const ProtoOps* dmr_ops();
 const ProtoOps* pocsag_ops();
 const ProtoOps* ysf_ops();
+const ProtoOps* nxdn_ops();
 
 }  // namespace dh

@@ -439,8 +439,68 @@ class YsfReplay: public MetaReplay {
         }
 };
 
+// ---- NXDN --------------------------------------------------------------------------------------------------------
+// Nxdn::MetaCollector (reference src/nxdn_decoder/nxdn_meta.cpp:6-76): every setter sends on its own unless held.
+class NxdnReplay: public MetaReplay {
+    public:
+        void apply(const DecEvent* ev, uint32_t n, std::string& out) override {
+            for (uint32_t i = 0; i < n; i++) {
+                const DecEvent& e = ev[i];
+                switch (e.kind) {
+                    case 1: setStr(sync, "voice", out); break;
+                    case 2:   // setFromSacch (nxdn_meta.cpp:54-66)
+                        setStr(type, e.a == 1 ? "conference" : (e.a == 2 ? "individual" : ""), out);
+                        setNum(source, (unsigned) e.data[0] << 8 | e.data[1], out);
+                        setNum(destination, (unsigned) e.data[2] << 8 | e.data[3], out);
+                        break;
+                    case 3:   // reset (nxdn_meta.cpp:68-75)
+                        held++;
+                        setStr(sync, "", out);
+                        setStr(type, "", out);
+                        setNum(source, 0, out);
+                        setNum(destination, 0, out);
+                        if (--held == 0) {
+                            if (dirty) send(out);
+                            dirty = false;
+                        }
+                        break;
+                }
+            }
+        }
+    private:
+        std::string sync, type;
+        unsigned source = 0, destination = 0;
+        int held = 0;
+        bool dirty = false;
+
+        void send(std::string& out) {
+            if (held) {
+                dirty = true;
+                return;
+            }
+            std::map<std::string, std::string> kv;
+            kv["protocol"] = "NXDN";
+            if (!sync.empty()) kv["sync"] = sync;
+            if (!type.empty()) kv["type"] = type;
+            if (source != 0) kv["source"] = std::to_string(source);
+            if (destination != 0) kv["destination"] = std::to_string(destination);
+            emit(kv, out);
+        }
+        void setStr(std::string& field, const std::string& v, std::string& out) {
+            if (field == v) return;
+            field = v;
+            send(out);
+        }
+        void setNum(unsigned& field, unsigned v, std::string& out) {
+            if (field == v) return;
+            field = v;
+            send(out);
+        }
+};
+
 }  // namespace
 
+MetaReplay* make_nxdn_replay() { return new NxdnReplay(); }
 MetaReplay* make_dmr_replay() { return new DmrReplay(); }
 MetaReplay* make_ysf_replay() { return new YsfReplay(); }
 

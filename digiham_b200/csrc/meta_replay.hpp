@@ -21,5 +21,6 @@ class MetaReplay {
 
 MetaReplay* make_dmr_replay();
 MetaReplay* make_ysf_replay();
+MetaReplay* make_nxdn_replay();
 
 }  // namespace dh

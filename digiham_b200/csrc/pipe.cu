@@ -3,6 +3,7 @@
 //   DMR / YSF : WideRrcFilter -> GfskDemodulator(10) -> decoder   (reference examples/dmr-decoder.sh:19-23,
 //                                                                  examples/ysf-decoder.sh:19-23)
 //   POCSAG    : FskDemodulator(40, invert) -> decoder             (reference examples/pocsag-decoder.sh:19-21)
+//   NXDN      : NarrowRrcFilter -> GfskDemodulator(20) -> decoder (reference examples/nxdn48-decoder.sh:19-23)
 //
 // In the reference every `|` is a process boundary with a 1024-item ring in between (src/lib/cli.cpp:10,101-106);
 // here the stages are kernels on one stream and each stage writes straight into the next stage's carry-aware
@@ -66,9 +67,10 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
     h->max_chunk = max_chunk;
     int rc = DH_OK;
     const bool pocsag = proto == DH_PROTO_POCSAG;
-    if (!pocsag) rc = dh_rrc_create(&h->rrc, device, channels, DH_RRC_WIDE);
+    const bool nxdn = proto == DH_PROTO_NXDN;
+    if (!pocsag) rc = dh_rrc_create(&h->rrc, device, channels, nxdn ? DH_RRC_NARROW : DH_RRC_WIDE);
     if (rc == DH_OK) rc = pocsag ? dh_demod_create(&h->demod, device, channels, 0, 40, 1)
-                                 : dh_demod_create(&h->demod, device, channels, 1, 10, 0);
+                                 : dh_demod_create(&h->demod, device, channels, 1, nxdn ? 20 : 10, 0);
     if (rc == DH_OK) rc = dh_decoder_create(&h->decoder, device, channels, proto);
     if (rc == DH_OK) rc = dh_demod_reserve(h->demod, max_chunk, &h->d_filt, &h->filt_pitch);
     if (rc == DH_OK) {

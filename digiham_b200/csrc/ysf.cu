@@ -13,6 +13,7 @@
 // register exchange, the whole decoded bit string travels with the state — word by word through __shfl_sync.
 // Metrics are kept modulo 256 like the reference's uint8_t (trellis.c:28,68).
 #include "decoder_ops.hpp"
+#include "viterbi.cuh"
 
 #define DH_TABLES_NO_HOST_ARRAYS
 #include "tables.inc"
@@ -117,52 +118,6 @@ __device__ __forceinline__ bool fec_golay24(uint32_t& w) {
     return e != 0;
 }
 
-// decode_trellis (trellis.c:32-109).  dibits[] (shared memory) holds `steps` received dibits; the decoded bit
-// string comes back MSB-first in out_words[0..5] (identical in every lane).  STEPS is 100 or 180.
-// Expected dibit of the transition prev -> (outbit, prev >> 1): linear in the bits of prev (trellis.c:8-25).
-template <int STEPS>
-__device__ __forceinline__ void viterbi(const uint8_t* dibits, int lane, uint32_t* out_words) {
-    constexpr int NW = (STEPS + 31) / 32;
-    const int state = lane & 15;
-    const uint32_t outbit = (uint32_t) (state >> 3) & 1u;
-    const int p0 = (state << 1) & 14;   // predecessor with k = 0; k = 1 is p0 | 1
-    auto expected = [](int prev, uint32_t ob) -> uint32_t {
-        uint32_t t = ob ? 3u : 0u;
-        if (prev & 1) t ^= 3u;
-        if (prev & 2) t ^= 2u;
-        if (prev & 4) t ^= 1u;
-        if (prev & 8) t ^= 1u;
-        return t;
-    };
-    const uint32_t e0 = expected(p0, outbit), e1 = expected(p0 | 1, outbit);
-    uint32_t metric = 0;
-    uint32_t surv[NW];
-#pragma unroll
-    for (int w = 0; w < NW; w++) surv[w] = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) {
-        const int lim = (STEPS - w * 32) < 32 ? (STEPS - w * 32) : 32;
-        for (int b = 0; b < lim; b++) {
-            const uint32_t in = dibits[w * 32 + b] & 3u;
-            const uint32_t m0 = (__shfl_sync(0xffffffffu, metric, p0) + __popc(in ^ e0)) & 0xFFu;
-            const uint32_t m1 = (__shfl_sync(0xffffffffu, metric, p0 | 1) + __popc(in ^ e1)) & 0xFFu;
-            const bool take1 = m1 < m0;
-            const int sel = take1 ? (p0 | 1) : p0;
-            metric = take1 ? m1 : m0;
-#pragma unroll
-            for (int v = 0; v <= w; v++) surv[v] = __shfl_sync(0xffffffffu, surv[v], sel);
-            surv[w] |= outbit << (31 - b);
-        }
-    }
-    // best = lowest state index with the minimal metric (trellis.c:94-98)
-    uint32_t key = (metric << 4) | (uint32_t) state;
-#pragma unroll
-    for (int d = 8; d >= 1; d >>= 1) key = min(key, __shfl_xor_sync(0xffffffffu, key, d));
-    const int best = (int) (key & 15u);
-#pragma unroll
-    for (int w = 0; w < NW; w++) out_words[w] = __shfl_sync(0xffffffffu, surv[w], best);
-}
-
 struct YCtx {
     YsfState st;
     DecWriter w;
@@ -201,7 +156,7 @@ __device__ bool parse_fich(YCtx& c, uint32_t& fich_out) {
     for (int i = c.lane; i < 100; i += 32) dib[i] = data[(i * 20) % 100 + (i * 20) / 100] & 3u;
     __syncwarp();
     uint32_t words[4];
-    viterbi<100>(dib, c.lane, words);
+    viterbi<100, false>(dib, c.lane, words);
     __syncwarp();
     uint32_t g[4];
     bool ok = true;
@@ -263,7 +218,7 @@ __device__ void v2_data_channel(YCtx& c, const uint8_t* payload, int frameNumber
     for (int i = c.lane; i < 100; i += 32) dib[i] = payload[(i % 5) * 72 + (i * 2) / 10] & 3u;
     __syncwarp();
     uint32_t words[4];
-    viterbi<100>(dib, c.lane, words);
+    viterbi<100, false>(dib, c.lane, words);
     __syncwarp();
     uint8_t raw[12];
 #pragma unroll
@@ -301,7 +256,7 @@ __device__ bool header_data_channel(YCtx& c, const uint8_t* in, uint8_t* dch20) 
     }
     __syncwarp();
     uint32_t words[6];
-    viterbi<180>(dib, c.lane, words);
+    viterbi<180, false>(dib, c.lane, words);
     __syncwarp();
     uint8_t raw[22];
 #pragma unroll

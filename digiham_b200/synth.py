@@ -588,3 +588,143 @@ def ysf_symbols(n_frames, seed=0, mode="DN", lead_in=None, symbol_errors=0.0):
         hit = rng.random(s.size) < symbol_errors
         s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# NXDN (reference src/nxdn_decoder/*): 192-dibit frames = FSW(10) + LICH(8) + SACCH(30) + 2 x 72 (voice pairs or
+# FACCH1); everything behind the FSW is scrambled by inverting the symbol when the PN9 output is 1.
+NXDN_FSW = np.array([3, 0, 3, 1, 3, 3, 1, 1, 2, 1], dtype=np.uint8)   # nxdn_phase.cpp:17
+
+
+def nxdn_scramble(dibits):
+    """Scrambler of src/nxdn_decoder/scrambler.cpp:12-25 (its own inverse): register 0b011100100."""
+    sr = 0b011100100
+    out = np.array(dibits, dtype=np.uint8)
+    for i in range(out.size):
+        wb = sr & 1
+        out[i] = (out[i] & 3) ^ (wb << 1)
+        fb = ((sr >> 4) & 1) ^ wb
+        sr = ((sr & 0b111111110) >> 1) | (fb << 8)
+    return out
+
+
+def nxdn_crc(bits, width, poly, init):
+    """Bit-serial CRC of sacch.cpp:76-90 (width 6, poly 0b010011) / facch1.cpp:60-75 (width 12, poly 0b10000000111)."""
+    crc = init
+    top = width - 1
+    mask = (1 << width) - 1
+    for b in bits:
+        cb = ((crc >> top) & 1) ^ int(b)
+        if cb:
+            crc ^= poly
+        crc = ((crc << 1) & (mask & ~1)) | cb
+    return crc
+
+
+def _nxdn_channel_encode(info_bits, crc_width, crc_poly, crc_init, punct, rows, cols):
+    """info + CRC + 4 tail zeros -> rate-1/2 K=5 code (same generator as YSF) -> puncture -> block interleave.
+    punct(i) is True for coded-bit positions that are NOT transmitted; the receiver reads tx[i * cols + k] as
+    punctured bit k * rows + i (sacch.cpp:45-54, facch1.cpp:34-43).  Returns dibits."""
+    info_bits = np.asarray(info_bits, dtype=np.uint8)
+    crc = nxdn_crc(info_bits, crc_width, crc_poly, crc_init)
+    bits = np.concatenate([info_bits, _int_to_bits(crc, crc_width), np.zeros(4, dtype=np.uint8)])
+    enc = ysf_conv_encode(bits)
+    coded = np.empty(2 * enc.size, dtype=np.uint8)
+    coded[0::2] = enc >> 1
+    coded[1::2] = enc & 1
+    kept = np.array([coded[i] for i in range(coded.size) if not punct(i)], dtype=np.uint8)
+    assert kept.size == rows * cols
+    tx = np.empty_like(kept)
+    for i in range(rows):
+        for k in range(cols):
+            tx[i * cols + k] = kept[k * rows + i]
+    return (tx[0::2] << 1) | tx[1::2]
+
+
+def nxdn_sacch_dibits(structure, ran, data18):
+    """structure: 0..3 = position in the superframe (SR field = structure ^ 3, sacch.cpp:18-20)."""
+    info = np.concatenate([_int_to_bits(structure ^ 3, 2), _int_to_bits(ran, 6), np.asarray(data18, dtype=np.uint8)])
+    return _nxdn_channel_encode(info, 6, 0b010011, 0b111111, lambda i: (i + 1) % 6 == 0, 12, 5)
+
+
+def nxdn_facch1_dibits(data80):
+    return _nxdn_channel_encode(data80, 12, 0b10000000111, 0xFFF, lambda i: (i - 1) % 4 == 0, 16, 9)
+
+
+def nxdn_lich_dibits(rf, functional, option, direction, rng, bad_parity=False):
+    """8 dibits: the LICH bit is the HIGH bit of each dibit (lich.cpp:10-13); low bits are 1 on air (+-3 symbols)."""
+    v = (rf << 5) | (functional << 3) | (option << 1) | direction
+    bits = _int_to_bits(v, 7)
+    par = int(bits[0] ^ bits[1] ^ bits[2] ^ bits[3]) ^ int(bad_parity)
+    bits = np.concatenate([bits, [par]]).astype(np.uint8)
+    return (bits << 1) | 1
+
+
+def nxdn_frame(lich, sacch, halves, rng):
+    """lich: 8 dibits, sacch: 30 dibits, halves: two arrays of 72 dibits -> one scrambled 192-dibit frame."""
+    body = np.concatenate([lich, sacch, halves[0], halves[1]]).astype(np.uint8)
+    return np.concatenate([NXDN_FSW, nxdn_scramble(body)])
+
+
+def nxdn_symbols(n_frames, seed=0, lead_in=None, symbol_errors=0.0):
+    """NXDN traffic: calls made of voice frames (SACCH superframes carrying VCALL with call type / source /
+    destination), FACCH1-stolen halves (IDLE and other message types), frames with broken LICH parity,
+    non-superframe SACCH, UDCH and RCCH frames, ended by a TX_RELEASE FACCH1; noise gaps in between."""
+    rng = np.random.default_rng(seed)
+    if lead_in is None:
+        lead_in = int(rng.integers(0, 400))
+    out = [rng.integers(0, 4, size=lead_in).astype(np.uint8)]
+    made = 0
+
+    def facch(msg_type):
+        d = rng.integers(0, 2, size=80).astype(np.uint8)
+        d[2:8] = _int_to_bits(msg_type, 6)
+        return nxdn_facch1_dibits(d)
+
+    while made < n_frames:
+        call_type = int(rng.choice([0b001, 0b100, 0b000, 0b110]))
+        src, dst = int(rng.integers(1, 65536)), int(rng.integers(0, 65536))
+        ran = int(rng.integers(0, 64))
+        msg = int(rng.choice([0x01, 0x01, 0x01, 0x07]))            # mostly VCALL
+        sf = np.concatenate([_int_to_bits(int(rng.integers(0, 4)), 2), _int_to_bits(msg, 6),
+                             _int_to_bits(int(rng.integers(0, 256)), 8), _int_to_bits(call_type, 3),
+                             _int_to_bits(int(rng.integers(0, 32)), 5), _int_to_bits(src, 16), _int_to_bits(dst, 16),
+                             _int_to_bits(int(rng.integers(0, 65536)), 16)])
+        n_call = int(rng.integers(8, 40))
+        for k in range(n_call):
+            structure = k % 4
+            r = rng.random()
+            rf, functional, option = 0b10, 0b10, 0b11
+            if r < 0.08:
+                option = int(rng.integers(0, 3))                   # one or both halves stolen by FACCH1
+            elif r < 0.11:
+                functional = 0b00                                  # non-superframe SACCH: not collected
+            elif r < 0.13:
+                functional = 0b01                                  # UDCH: frame skipped
+            elif r < 0.15:
+                rf = 0b00                                          # RCCH: frame skipped
+            lich = nxdn_lich_dibits(rf, functional, option, int(rng.integers(0, 2)), rng,
+                                    bad_parity=rng.random() < 0.05)
+            sacch = nxdn_sacch_dibits(structure, ran, sf[18 * structure:18 * structure + 18])
+            halves = []
+            for i in range(2):
+                if (option >> (1 - i)) & 1:
+                    halves.append(rng.integers(0, 4, size=72).astype(np.uint8))
+                else:
+                    halves.append(facch(int(rng.choice([0x10, 0x10, 0x01, 0x3F]))))
+            out.append(nxdn_frame(lich, sacch, halves, rng))
+            made += 1
+        # end of call: TX_RELEASE in the first or second half
+        which = int(rng.integers(0, 2))
+        halves = [facch(0x08) if which == 0 else rng.integers(0, 4, size=72).astype(np.uint8),
+                  facch(0x08) if which == 1 else facch(0x10)]
+        option = 0b00 if which == 0 else 0b10
+        lich = nxdn_lich_dibits(0b10, 0b10, option, 0, rng)
+        out.append(nxdn_frame(lich, nxdn_sacch_dibits(n_call % 4, ran, sf[0:18]), halves, rng))
+        made += 1
+        out.append(rng.integers(0, 4, size=int(rng.integers(0, 500))).astype(np.uint8))
+    s = np.concatenate(out)
+    if symbol_errors > 0:
+        hit = rng.random(s.size) < symbol_errors
+        s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
+    return s

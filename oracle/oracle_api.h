@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-enum { ORC_PROTO_DMR = 0, ORC_PROTO_YSF = 1, ORC_PROTO_POCSAG = 2 };
+enum { ORC_PROTO_DMR = 0, ORC_PROTO_YSF = 1, ORC_PROTO_POCSAG = 2, ORC_PROTO_NXDN = 3, ORC_PROTO_DSTAR = 4 };
 
 enum {
     ORC_FEC_HAMMING_7_4 = 0,
@@ -48,14 +48,16 @@ size_t orc_rrc(int narrow, const float* in, size_t n, size_t chunk, float* out);
 size_t orc_demod(int four_level, unsigned sps, int invert, const float* in, size_t n, size_t chunk,
                  uint8_t* out, size_t out_cap);
 
-/* Dmr::Decoder / Ysf::Decoder / Pocsag::Decoder on a symbol stream.  Returns #bytes written to out.
+/* Dmr:: / Ysf:: / Pocsag:: / Nxdn:: / DStar::Decoder on a symbol stream.  Returns #bytes written to out.
  * meta receives the concatenated StringSerializer lines of a MetaWriter attached before the first
  * symbol; *meta_len the byte count (truncated at meta_cap).  slot_filter only applies to DMR. */
 size_t orc_decode(int proto, const uint8_t* sym, size_t n, size_t chunk, int slot_filter,
                   uint8_t* out, size_t out_cap, char* meta, size_t meta_cap, size_t* meta_len);
 
 /* The whole pipe of one channel, wired like examples/{dmr,ysf,pocsag}-decoder.sh:
- *   DMR/YSF: WideRrcFilter -> GfskDemodulator(10) -> decoder;  POCSAG: FskDemodulator(40, true) -> decoder.
+ *   DMR/YSF: WideRrcFilter -> GfskDemodulator(10) -> decoder;  POCSAG: FskDemodulator(40, true) -> decoder;
+ *   NXDN: NarrowRrcFilter -> GfskDemodulator(20) -> decoder (examples/nxdn48-decoder.sh:19-23);
+ *   D-Star: FskDemodulator(10) -> decoder (examples/dstar-decoder.sh:19-21).
  * sym_out (nullable) receives the demodulator output. */
 size_t orc_pipe(int proto, const float* in, size_t n, size_t chunk, int slot_filter,
                 uint8_t* sym_out, size_t sym_cap, size_t* n_sym,
@@ -84,6 +86,17 @@ unsigned orc_trellis(const uint8_t* in, unsigned steps, uint8_t* out);
 uint16_t orc_crc16(const uint8_t* data, int count);
 void orc_whitening(const uint8_t* in, uint8_t* out, unsigned nbits);
 unsigned orc_hamming_distance(const uint8_t* a, const uint8_t* b, size_t n);
+
+/* Nxdn::Trellis::decode (src/nxdn_decoder/trellis.cpp:29-101): len input BITS (len/2 dibits packed 4 per byte,
+ * MSB first), (len+15)/16 bytes out, returns the best metric. */
+unsigned orc_nxdn_trellis(const uint8_t* in, unsigned len, uint8_t* out);
+/* Nxdn::Sacch::parse on 30 descrambled dibits (sacch.cpp:24-43): 1 + writes the 5 decoded bytes, or 0. */
+int orc_nxdn_sacch(const uint8_t in[30], uint8_t out[5]);
+/* Nxdn::Facch1::parse on 72 descrambled dibits (facch1.cpp:8-26): returns the message type, or -1. */
+int orc_nxdn_facch1(const uint8_t in[72]);
+/* DStar::Header::parseFromHeader on 660 raw bits (header.cpp:23-48): -1 when rejected, else isData() and
+ * Header::toString() in text (NUL-terminated, truncated at cap). */
+int orc_dstar_header(const uint8_t in[660], char* text, size_t cap);
 
 #ifdef __cplusplus
 }

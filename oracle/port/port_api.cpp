@@ -25,6 +25,7 @@ void decode(int proto, const uint8_t* sym, size_t n, int slotFilter, port::Decod
         case ORC_PROTO_DMR: port::decode_dmr(sym, n, slotFilter, d); break;
         case ORC_PROTO_YSF: port::decode_ysf(sym, n, d); break;
         case ORC_PROTO_POCSAG: port::decode_pocsag(sym, n, d); break;
+        case ORC_PROTO_NXDN: port::decode_nxdn(sym, n, d); break;
     }
 }
 
@@ -63,10 +64,11 @@ size_t orc_pipe(int proto, const float* in, size_t n, size_t, int slot_filter, u
         port::Demod d(40, false, true);
         d.run(in, n, sym);
     } else {
-        port::Rrc f(false);
+        const bool nxdn = proto == ORC_PROTO_NXDN;
+        port::Rrc f(nxdn);
         std::vector<float> filtered(n);
         for (size_t i = 0; i < n; i++) filtered[i] = f.step(in[i]);
-        port::Demod d(10, true, false);
+        port::Demod d(nxdn ? 20 : 10, true, false);
         d.run(filtered.data(), n, sym);
     }
     if (n_sym) *n_sym = sym.size();
@@ -123,5 +125,8 @@ unsigned orc_trellis(const uint8_t* in, unsigned steps, uint8_t* out) { return p
 uint16_t orc_crc16(const uint8_t* data, int count) { return port::crc16(data, count); }
 void orc_whitening(const uint8_t* in, uint8_t* out, unsigned nbits) { port::dewhiten(in, out, nbits); }
 unsigned orc_hamming_distance(const uint8_t* a, const uint8_t* b, size_t n) { return port::hamming_distance(a, b, n); }
+unsigned orc_nxdn_trellis(const uint8_t* in, unsigned len, uint8_t* out) { return port::nxdn_viterbi(in, len, out); }
+int orc_nxdn_sacch(const uint8_t in[30], uint8_t out[5]) { return port::nxdn_sacch_probe(in, out); }
+int orc_nxdn_facch1(const uint8_t in[72]) { return port::nxdn_facch1_probe(in); }
 
 }

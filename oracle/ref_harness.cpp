@@ -16,7 +16,13 @@
 #include "dmr_decoder.hpp"
 #include "ysf_decoder.hpp"
 #include "pocsag_decoder.hpp"
+#include "nxdn_decoder.hpp"
+#include "dstar_decoder.hpp"
 #include "meta.hpp"
+#include "nxdn_decoder/trellis.hpp"
+#include "nxdn_decoder/sacch.hpp"
+#include "nxdn_decoder/facch1.hpp"
+#include "dstar_decoder/header.hpp"
 
 extern "C" {
 #include "hamming_distance.h"
@@ -138,6 +144,10 @@ namespace {
                 return makeZeroed<Digiham::Ysf::Decoder>();
             case ORC_PROTO_POCSAG:
                 return makeZeroed<Digiham::Pocsag::Decoder>();
+            case ORC_PROTO_NXDN:
+                return makeZeroed<Digiham::Nxdn::Decoder>();
+            case ORC_PROTO_DSTAR:
+                return makeZeroed<Digiham::DStar::Decoder>();
         }
         return nullptr;
     }
@@ -222,6 +232,8 @@ size_t orc_pipe(int proto, const float* in, size_t n, size_t chunk, int slot_fil
                 uint8_t* out, size_t out_cap, char* meta, size_t meta_cap, size_t* meta_len) {
     std::string metaText;
     const bool pocsag = proto == ORC_PROTO_POCSAG;
+    const bool dstar = proto == ORC_PROTO_DSTAR;
+    const bool nxdn = proto == ORC_PROTO_NXDN;
 
     // stage buffers: each stage writes into a vector the next stage reads from
     SpanReader<float> rIn(in);
@@ -237,6 +249,17 @@ size_t orc_pipe(int proto, const float* in, size_t n, size_t chunk, int slot_fil
         // examples/pocsag-decoder.sh:19-21: fsk_demodulator -i -s 40 | pocsag_decoder
         demod = makeZeroed<Digiham::Fsk::FskDemodulator>(40u, true);
         demod->setReader(&rIn);
+    } else if (dstar) {
+        // examples/dstar-decoder.sh:19-21: fsk_demodulator -s 10 | dstar_decoder
+        demod = makeZeroed<Digiham::Fsk::FskDemodulator>(10u, false);
+        demod->setReader(&rIn);
+    } else if (nxdn) {
+        // examples/nxdn48-decoder.sh:19-23: rrc_filter -n | gfsk_demodulator -s 20 | nxdn_decoder
+        rrc = makeZeroed<Digiham::RrcFilter::NarrowRrcFilter>();
+        rrc->setReader(&rIn);
+        rrc->setWriter(&wFilt);
+        demod = makeZeroed<Digiham::Fsk::GfskDemodulator>(20u);
+        demod->setReader(&rFilt);
     } else {
         // examples/dmr-decoder.sh:19-23, examples/ysf-decoder.sh:19-23: rrc_filter | gfsk_demodulator
         rrc = makeZeroed<Digiham::RrcFilter::WideRrcFilter>();
@@ -273,10 +296,11 @@ size_t orc_pipe(int proto, const float* in, size_t n, size_t chunk, int slot_fil
 
     dec->~Decoder();
     std::free(dec);
-    if (pocsag) destroyZeroed((Digiham::Fsk::FskDemodulator*) demod);
+    if (pocsag || dstar) destroyZeroed((Digiham::Fsk::FskDemodulator*) demod);
     else {
         destroyZeroed((Digiham::Fsk::GfskDemodulator*) demod);
-        destroyZeroed((Digiham::RrcFilter::WideRrcFilter*) rrc);
+        if (nxdn) destroyZeroed((Digiham::RrcFilter::NarrowRrcFilter*) rrc);
+        else destroyZeroed((Digiham::RrcFilter::WideRrcFilter*) rrc);
     }
     return produced;
 }
@@ -375,6 +399,41 @@ void orc_whitening(const uint8_t* in, uint8_t* out, unsigned nbits) {
 
 unsigned orc_hamming_distance(const uint8_t* a, const uint8_t* b, size_t n) {
     return hamming_distance(const_cast<uint8_t*>(a), const_cast<uint8_t*>(b), n);
+}
+
+unsigned orc_nxdn_trellis(const uint8_t* in, unsigned len, uint8_t* out) {
+    Digiham::Nxdn::Trellis t;
+    return t.decode(const_cast<uint8_t*>(in), out, len);
+}
+
+int orc_nxdn_sacch(const uint8_t in[30], uint8_t out[5]) {
+    Digiham::Nxdn::Sacch* s = Digiham::Nxdn::Sacch::parse(const_cast<uint8_t*>(in));
+    if (s == nullptr) return 0;
+    std::memcpy(out, s->getSuperframeData() - 1, 5);
+    delete s;
+    return 1;
+}
+
+int orc_nxdn_facch1(const uint8_t in[72]) {
+    Digiham::Nxdn::Facch1* f = Digiham::Nxdn::Facch1::parse(const_cast<uint8_t*>(in));
+    if (f == nullptr) return -1;
+    int t = f->getMessageType();
+    delete f;
+    return t;
+}
+
+int orc_dstar_header(const uint8_t in[660], char* text, size_t cap) {
+    Digiham::DStar::Header* h = Digiham::DStar::Header::parseFromHeader(const_cast<uint8_t*>(in));
+    if (h == nullptr) return -1;
+    std::string s = h->toString();
+    if (text && cap) {
+        size_t n = s.size() < cap - 1 ? s.size() : cap - 1;
+        std::memcpy(text, s.data(), n);
+        text[n] = 0;
+    }
+    int r = h->isData() ? 1 : 0;
+    delete h;
+    return r;
 }
 
 }

@@ -16,7 +16,7 @@ ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_SO = os.path.join(ORACLE_DIR, "_ref", "libdigiham_ref.so")
 PORT_SO = os.path.join(ORACLE_DIR, "liboracle_port.so")
 
-PROTO_DMR, PROTO_YSF, PROTO_POCSAG = 0, 1, 2
+PROTO_DMR, PROTO_YSF, PROTO_POCSAG, PROTO_NXDN, PROTO_DSTAR = 0, 1, 2, 3, 4
 FEC_NAMES = ["hamming_7_4", "hamming_13_9", "hamming_15_11", "hamming_16_11", "qr_16_7", "golay_20_8",
              "golay_24_12", "bch_31_21"]
 FEC_BITS = [7, 13, 15, 16, 16, 20, 24, 31]
@@ -55,6 +55,13 @@ def _bind(path):
     L.orc_whitening.restype = None
     L.orc_hamming_distance.restype = ctypes.c_uint
     L.orc_hamming_distance.argtypes = [_vp, _vp, _sz]
+    if hasattr(L, "orc_nxdn_trellis"):
+        L.orc_nxdn_trellis.restype = ctypes.c_uint
+        L.orc_nxdn_trellis.argtypes = [_vp, ctypes.c_uint, _vp]
+        L.orc_nxdn_sacch.argtypes = [_vp, _vp]
+        L.orc_nxdn_facch1.argtypes = [_vp]
+    if hasattr(L, "orc_dstar_header"):
+        L.orc_dstar_header.argtypes = [_vp, _vp, _sz]
     return L
 
 
@@ -150,6 +157,28 @@ class Oracle:
         out = np.zeros((steps + 7) // 8, dtype=np.uint8)
         metric = self.L.orc_trellis(p.ctypes.data, steps, out.ctypes.data)
         return metric, out
+
+    def nxdn_trellis(self, packed, nbits):
+        p = np.ascontiguousarray(packed, dtype=np.uint8)
+        out = np.zeros((nbits + 15) // 16, dtype=np.uint8)
+        metric = self.L.orc_nxdn_trellis(p.ctypes.data, nbits, out.ctypes.data)
+        return metric, out
+
+    def nxdn_sacch(self, dibits30):
+        d = np.ascontiguousarray(dibits30, dtype=np.uint8)
+        out = np.zeros(5, dtype=np.uint8)
+        ok = self.L.orc_nxdn_sacch(d.ctypes.data, out.ctypes.data)
+        return bool(ok), out
+
+    def nxdn_facch1(self, dibits72):
+        d = np.ascontiguousarray(dibits72, dtype=np.uint8)
+        return self.L.orc_nxdn_facch1(d.ctypes.data)
+
+    def dstar_header(self, bits660):
+        d = np.ascontiguousarray(bits660, dtype=np.uint8)
+        text = ctypes.create_string_buffer(512)
+        rc = self.L.orc_dstar_header(d.ctypes.data, text, 512)
+        return rc, text.value
 
     def crc16(self, data):
         d = np.ascontiguousarray(data, dtype=np.uint8)
