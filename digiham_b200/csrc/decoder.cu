@@ -195,6 +195,7 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
         case DH_PROTO_POCSAG: ops = dh::pocsag_ops(); break;
         case DH_PROTO_YSF: ops = dh::ysf_ops(); break;
         case DH_PROTO_NXDN: ops = dh::nxdn_ops(); break;
+        case DH_PROTO_DSTAR: ops = dh::dstar_ops(); break;
         default: break;
     }
     DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "dh_decoder_create: protocol %d not supported", proto);
@@ -374,6 +375,7 @@ int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, 
         case DH_PROTO_DMR: r = dh::make_dmr_replay(); break;
         case DH_PROTO_YSF: r = dh::make_ysf_replay(); break;
         case DH_PROTO_NXDN: r = dh::make_nxdn_replay(); break;
+        case DH_PROTO_DSTAR: r = dh::make_dstar_replay(); break;
         default: break;
     }
     DH_REQUIRE(r != nullptr, DH_E_UNSUPPORTED, "dh_meta_replay: protocol %d has no metadata replay", proto);

@@ -22,5 +22,6 @@ const ProtoOps* dmr_ops();
 const ProtoOps* pocsag_ops();
 const ProtoOps* ysf_ops();
 const ProtoOps* nxdn_ops();
+const ProtoOps* dstar_ops();
 
 }  // namespace dh

@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <vector>
+#include <cstdlib>
 
 namespace dh {
 
@@ -498,8 +500,206 @@ class NxdnReplay: public MetaReplay {
         }
 };
 
+// ---- D-Star ------------------------------------------------------------------------------------------------------
+// Host half of DStar::VoicePhase (reference src/dstar_decoder/dstar_phase.cpp:151-278: slow-data reassembly, DPRS
+// and NMEA sentences), Header's callsign getters (header.cpp:150-178) and DStar::MetaCollector
+// (dstar_meta.cpp:5-130).  Where the reference would throw or index out of range (std::stof on a non-numeric NMEA
+// field, fewer than six GGA fields) the sentence is skipped.
+class DstarReplay: public MetaReplay {
+    public:
+        void apply(const DecEvent* ev, uint32_t n, std::string& out) override {
+            for (uint32_t i = 0; i < n; i++) {
+                const DecEvent& e = ev[i];
+                switch (e.kind) {
+                    case 1:
+                        if (e.a < 4) std::memcpy(radioHeader + 12 * e.a, e.data, e.a < 3 ? 12 : 5);
+                        if (e.a == 3) setFromHeader(radioHeader, out);
+                        break;
+                    case 2:
+                        resetFrames();
+                        simpleData.clear();
+                        break;
+                    case 3: collect(e.data); break;
+                    case 4:
+                        if (e.a) set(sync, "voice", out);
+                        parseFrameData(out);
+                        resetFrames();
+                        break;
+                    case 5: reset(out); break;
+                }
+            }
+        }
+    private:
+        std::string sync, message, departure, destination, ourCall, yourCall, dprs;
+        bool located = false;
+        float lat = 0, lon = 0;
+        int held = 0;
+        bool dirty = false;
+        unsigned char radioHeader[41] = {0};
+        unsigned char msg[20] = {0};
+        unsigned msgBlocks = 0;
+        unsigned char hdr[41] = {0};
+        unsigned hdrCount = 0;
+        std::string simpleData;
+
+        void send(std::string& out) {
+            if (held) {
+                dirty = true;
+                return;
+            }
+            std::map<std::string, std::string> kv;
+            kv["protocol"] = "DSTAR";
+            if (!sync.empty()) kv["sync"] = sync;
+            if (!departure.empty()) kv["departure"] = departure;
+            if (!destination.empty()) kv["destination"] = destination;
+            if (!ourCall.empty()) kv["ourcall"] = ourCall;
+            if (!yourCall.empty()) kv["yourcall"] = yourCall;
+            if (!message.empty()) kv["message"] = message;
+            if (!dprs.empty()) kv["dprs"] = dprs;
+            if (located) {
+                kv["lat"] = std::to_string(lat);
+                kv["lon"] = std::to_string(lon);
+            }
+            emit(kv, out);
+        }
+        void set(std::string& field, const std::string& v, std::string& out) {
+            if (field == v) return;
+            field = v;
+            send(out);
+        }
+        void setGps(bool valid, float la, float lo, std::string& out) {
+            if (!valid && !located) return;
+            if (valid && located && lat == la && lon == lo) return;
+            located = valid;
+            lat = la;
+            lon = lo;
+            send(out);
+        }
+        void release(std::string& out) {
+            if (--held == 0) {
+                if (dirty) send(out);
+                dirty = false;
+            }
+        }
+        void reset(std::string& out) {
+            held++;
+            set(sync, "", out);
+            set(message, "", out);
+            set(departure, "", out);
+            set(destination, "", out);
+            set(ourCall, "", out);
+            set(yourCall, "", out);
+            set(dprs, "", out);
+            setGps(false, 0, 0, out);
+            release(out);
+        }
+        static std::string field(const unsigned char* p, size_t n) {
+            std::string s = latin1_to_utf8(p, n);
+            s.erase(s.find_last_not_of(' ') + 1);
+            return s;
+        }
+        void setFromHeader(const unsigned char* h, std::string& out) {
+            held++;
+            set(sync, (h[0] >> 7) & 1 ? "data" : "voice", out);
+            set(departure, field(h + 11, 8), out);
+            set(destination, field(h + 3, 8), out);
+            std::string own = field(h + 27, 8);
+            const std::string suffix = field(h + 35, 4);
+            if (!suffix.empty()) own += "/" + suffix;
+            set(ourCall, own, out);
+            set(yourCall, field(h + 19, 8), out);
+            release(out);
+        }
+        void resetFrames() {
+            std::memset(msg, 0, sizeof(msg));
+            msgBlocks = 0;
+            std::memset(hdr, 0, sizeof(hdr));
+            hdrCount = 0;
+        }
+        void collect(const unsigned char* block) {
+            const unsigned n = block[0] & 0x0F;
+            switch (block[0] >> 4) {
+                case 4:
+                    if (n > 3) break;
+                    std::memcpy(msg + n * 5, block + 1, 5);
+                    msgBlocks |= 1u << n;
+                    break;
+                case 5:
+                    if (n > 5 || hdrCount + n > 41) break;
+                    std::memcpy(hdr + hdrCount, block + 1, n);
+                    hdrCount += n;
+                    break;
+                case 3:
+                    if (n > 5) break;
+                    simpleData.append(reinterpret_cast<const char*>(block + 1), n);
+                    break;
+                default: break;
+            }
+        }
+        static unsigned crcOf(const unsigned char* data, size_t len) {
+            unsigned c = 0xFFFF;
+            for (size_t k = 0; k < len; k++) {
+                for (int i = 0; i < 8; i++) {
+                    c ^= (data[k] >> i) & 1u;
+                    c = (c & 1u) ? ((c >> 1) ^ 0x8408u) : (c >> 1);
+                }
+            }
+            return c ^ 0xFFFFu;
+        }
+        void parseNmea(const std::string& input, std::string& out) {
+            const size_t star = input.find_last_of('*');
+            if (star == std::string::npos || star + 2 > input.length()) return;
+            const std::string body = input.substr(1, star - 1);
+            if (body.length() < 2) return;
+            unsigned checksum = 0;
+            for (char ch : body) checksum ^= (unsigned char) ch;
+            if (checksum != (unsigned) std::strtoul(input.substr(star + 1, 2).c_str(), nullptr, 16)) return;
+            std::vector<std::string> fields;
+            size_t from = 0;
+            while (from <= body.length()) {
+                const size_t comma = body.find(',', from);
+                if (comma == std::string::npos) {
+                    if (from < body.length()) fields.push_back(body.substr(from));
+                    break;
+                }
+                fields.push_back(body.substr(from, comma - from));
+                from = comma + 1;
+            }
+            if (body.substr(2, 3) != "GGA" || fields.size() < 6) return;
+            char* end = nullptr;
+            const float latC = std::strtof(fields[2].c_str(), &end);
+            if (end == fields[2].c_str()) return;
+            const float lonC = std::strtof(fields[4].c_str(), &end);
+            if (end == fields[4].c_str()) return;
+            float la = (float) ((int) latC / 100);
+            la += (latC - la * 100) / 60;
+            if (fields[3] == "S") la *= -1;
+            float lo = (float) ((int) lonC / 100);
+            lo += (lonC - lo * 100) / 60;
+            if (fields[5] == "W") lo *= -1;
+            setGps(true, la, lo, out);
+        }
+        void parseFrameData(std::string& out) {
+            if (msgBlocks == 0x0F) set(message, latin1_to_utf8(msg, 20), out);
+            if (hdrCount == 41 && crcOf(hdr, 39) == ((unsigned) hdr[39] | (unsigned) hdr[40] << 8)) setFromHeader(hdr, out);
+            size_t pos;
+            while ((pos = simpleData.find('\r')) != std::string::npos) {
+                const std::string s = simpleData.substr(0, pos + 1);
+                if (s.length() >= 10 && s.compare(0, 5, "$$CRC") == 0 && s[9] == ',') {
+                    const unsigned check = (unsigned) std::strtoul(s.substr(5, 4).c_str(), nullptr, 16);
+                    if (crcOf(reinterpret_cast<const unsigned char*>(s.data()) + 10, s.length() - 10) == (check & 0xFFFFu))
+                        set(dprs, s.substr(10, s.length() - 11), out);
+                } else if (s.length() > 5 && s[0] == '$') {
+                    parseNmea(s, out);
+                }
+                simpleData = simpleData.substr(pos + 1 + (simpleData.length() > pos + 1 && simpleData[pos + 1] == '\n'));
+            }
+        }
+};
+
 }  // namespace
 
+MetaReplay* make_dstar_replay() { return new DstarReplay(); }
 MetaReplay* make_nxdn_replay() { return new NxdnReplay(); }
 MetaReplay* make_dmr_replay() { return new DmrReplay(); }
 MetaReplay* make_ysf_replay() { return new YsfReplay(); }

@@ -22,5 +22,6 @@ class MetaReplay {
 MetaReplay* make_dmr_replay();
 MetaReplay* make_ysf_replay();
 MetaReplay* make_nxdn_replay();
+MetaReplay* make_dstar_replay();
 
 }  // namespace dh

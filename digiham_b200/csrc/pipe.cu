@@ -4,6 +4,7 @@
 //                                                                  examples/ysf-decoder.sh:19-23)
 //   POCSAG    : FskDemodulator(40, invert) -> decoder             (reference examples/pocsag-decoder.sh:19-21)
 //   NXDN      : NarrowRrcFilter -> GfskDemodulator(20) -> decoder (reference examples/nxdn48-decoder.sh:19-23)
+//   D-Star    : FskDemodulator(10) -> decoder                     (reference examples/dstar-decoder.sh:19-21)
 //
 // In the reference every `|` is a process boundary with a 1024-item ring in between (src/lib/cli.cpp:10,101-106);
 // here the stages are kernels on one stream and each stage writes straight into the next stage's carry-aware
@@ -68,9 +69,13 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
     int rc = DH_OK;
     const bool pocsag = proto == DH_PROTO_POCSAG;
     const bool nxdn = proto == DH_PROTO_NXDN;
-    if (!pocsag) rc = dh_rrc_create(&h->rrc, device, channels, nxdn ? DH_RRC_NARROW : DH_RRC_WIDE);
-    if (rc == DH_OK) rc = pocsag ? dh_demod_create(&h->demod, device, channels, 0, 40, 1)
-                                 : dh_demod_create(&h->demod, device, channels, 1, nxdn ? 20 : 10, 0);
+    const bool dstar = proto == DH_PROTO_DSTAR;
+    if (!pocsag && !dstar) rc = dh_rrc_create(&h->rrc, device, channels, nxdn ? DH_RRC_NARROW : DH_RRC_WIDE);
+    if (rc == DH_OK) {
+        if (pocsag) rc = dh_demod_create(&h->demod, device, channels, 0, 40, 1);
+        else if (dstar) rc = dh_demod_create(&h->demod, device, channels, 0, 10, 0);
+        else rc = dh_demod_create(&h->demod, device, channels, 1, nxdn ? 20 : 10, 0);
+    }
     if (rc == DH_OK) rc = dh_decoder_create(&h->decoder, device, channels, proto);
     if (rc == DH_OK) rc = dh_demod_reserve(h->demod, max_chunk, &h->d_filt, &h->filt_pitch);
     if (rc == DH_OK) {

@@ -728,3 +728,169 @@ def nxdn_symbols(n_frames, seed=0, lead_in=None, symbol_errors=0.0):
         hit = rng.random(s.size) < symbol_errors
         s = np.where(hit, s ^ rng.integers(1, 4, size=s.size).astype(np.uint8), s).astype(np.uint8)
     return s
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# D-Star (reference src/dstar_decoder/*): 4800 bit/s, one bit per symbol.  Transmission = bit sync, frame sync,
+# 660-bit radio header (K=3 rate-1/2 code, 24-row interleave, scrambler), then 96-bit frames of 72 voice bits + 24
+# slow-data bits (every 21st data field is the voice sync), closed by the 48-bit terminator.
+DSTAR_HEADER_SYNC = np.array([0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 1, 0, 1, 1, 0, 0, 1, 0, 1, 0, 0, 0, 0], dtype=np.uint8)
+DSTAR_VOICE_SYNC = np.array([1, 0, 1, 0, 1, 0, 1, 0, 1, 0, 1, 1, 0, 1, 0, 0, 0, 1, 1, 0, 1, 0, 0, 0], dtype=np.uint8)
+DSTAR_TERMINATOR = np.array([1, 0] * 16 + [0, 0, 0, 1, 0, 0, 1, 1, 0, 1, 0, 1, 1, 1, 1, 0], dtype=np.uint8)
+
+
+def dstar_scramble(bits):
+    """src/dstar_decoder/scrambler.cpp:6-21 (its own inverse): register 0b1111111, output bit0 ^ bit3."""
+    sr = 0b1111111
+    out = np.array(bits, dtype=np.uint8) & 1
+    for i in range(out.size):
+        wb = (sr & 1) ^ ((sr >> 3) & 1)
+        out[i] ^= wb
+        sr = ((sr & 0b1111110) >> 1) | (wb << 6)
+    return out
+
+
+def dstar_crc(data):
+    """src/dstar_decoder/crc.cpp:6-23: reflected CCITT (0x8408), init 0xFFFF, inverted."""
+    c = 0xFFFF
+    for byte in data:
+        for i in range(8):
+            c ^= (int(byte) >> i) & 1
+            c = (c >> 1) ^ 0x8408 if c & 1 else c >> 1
+    return c ^ 0xFFFF
+
+
+def _lsb_bits(data):
+    return np.unpackbits(np.asarray(data, dtype=np.uint8), bitorder="little")
+
+
+def dstar_header_bytes(flags=(0, 0, 0), rpt2="DB0XYZ G", rpt1="DB0XYZ B", your="CQCQCQ", my="DL1ABC", suffix="B200"):
+    def f(t, n):
+        b = t.encode("latin-1")[:n]
+        return b + b" " * (n - len(b))
+    body = bytes(flags) + f(rpt2, 8) + f(rpt1, 8) + f(your, 8) + f(my, 8) + f(suffix, 4)
+    crc = dstar_crc(body)
+    return np.frombuffer(body + bytes([crc & 0xFF, crc >> 8]), dtype=np.uint8)
+
+
+def dstar_header_bits(header41):
+    """41 bytes -> 660 channel bits (header.cpp:23-48 backwards: bits LSB first, K=3 code of
+    Header::trellis_transitions, interleave, scramble)."""
+    bits = np.concatenate([_lsb_bits(header41), np.zeros(2, dtype=np.uint8)])
+    state = 0
+    coded = np.zeros(660, dtype=np.uint8)
+    for i, b in enumerate(bits):
+        t = 3 if b else 0
+        if state & 1:
+            t ^= 3
+        if state & 2:
+            t ^= 2
+        coded[2 * i] = t >> 1
+        coded[2 * i + 1] = t & 1
+        state = (int(b) << 1) | (state >> 1)
+    tx = np.zeros(660, dtype=np.uint8)
+    for i in range(12):
+        for k in range(28):
+            tx[i * 28 + k] = coded[k * 24 + i]
+    for i in range(12, 24):
+        for k in range(27):
+            tx[12 + i * 27 + k] = coded[k * 24 + i]
+    return dstar_scramble(tx)
+
+
+def dstar_slow_data_blocks(message=None, header41=None, text=None):
+    """6-byte slow-data blocks (mini header + 5 bytes, dstar_phase.cpp:163-211)."""
+    blocks = []
+    if message is not None:
+        m = message.encode("latin-1")[:20]
+        m = m + b" " * (20 - len(m))
+        for k in range(4):
+            blocks.append(bytes([0x40 | k]) + m[5 * k:5 * k + 5])
+    if header41 is not None:
+        h = bytes(header41)
+        for k in range(0, 41, 5):
+            part = h[k:k + 5]
+            blocks.append(bytes([0x50 | len(part)]) + part + b"\x66" * (5 - len(part)))
+    if text is not None:
+        t = text.encode("latin-1")
+        for k in range(0, len(t), 5):
+            part = t[k:k + 5]
+            blocks.append(bytes([0x30 | len(part)]) + part + b"\x66" * (5 - len(part)))
+    return blocks
+
+
+def dstar_gga(lat=4807.038, lon=1131.0, south=False, west=False):
+    body = "GPGGA,123519,%09.4f,%s,%010.4f,%s,1,08,0.9,545.4,M,46.9,M,," % (lat, "S" if south else "N", lon,
+                                                                              "W" if west else "E")
+    cs = 0
+    for ch in body:
+        cs ^= ord(ch)
+    return "$%s*%02X\r\n" % (body, cs)
+
+
+def dstar_dprs(payload="DL1ABC-7>API282,DSTAR*:!4807.03N/01131.00E>B200 test"):
+    body = payload + "\r"
+    return "$$CRC%04X,%s" % (dstar_crc(body.encode("latin-1")), body)
+
+
+def dstar_symbols(n_frames, seed=0, lead_in=None, bit_errors=0.0):
+    """D-Star traffic: transmissions with radio header (voice, some data headers, some with a broken CRC), voice
+    frames carrying slow data (20-character message, header resend, DPRS and NMEA GGA sentences, filler), late
+    entry (voice sync without header), terminators (full and second half only), noise gaps."""
+    rng = np.random.default_rng(seed)
+    calls = ["DL1ABC", "W1AW", "JA1YSF", "OE1XYZ", "G4KLX"]
+    if lead_in is None:
+        lead_in = int(rng.integers(0, 300))
+    out = [rng.integers(0, 2, size=lead_in).astype(np.uint8)]
+    made = 0
+    while made < n_frames:
+        my = calls[int(rng.integers(0, len(calls)))]
+        flags = (0x80 if rng.random() < 0.1 else 0x00, 0, 0)
+        hdr = dstar_header_bytes(flags=flags, my=my, your=calls[int(rng.integers(0, len(calls)))],
+                                 suffix=["B200", "", "ID51"][int(rng.integers(0, 3))])
+        late_entry = rng.random() < 0.2
+        if not late_entry:
+            hb = dstar_header_bits(hdr)
+            if rng.random() < 0.1:
+                hb = hb.copy()
+                hb[rng.choice(660, size=40, replace=False)] ^= 1      # uncorrectable header
+            out.append(np.concatenate([np.tile([1, 0], 32).astype(np.uint8), DSTAR_HEADER_SYNC[9:], hb]))
+        blocks = []
+        r = rng.random()
+        if r < 0.5:
+            blocks += dstar_slow_data_blocks(message="B200 msg %d %s" % (made, my))
+        if r > 0.3:
+            blocks += dstar_slow_data_blocks(header41=hdr)
+        if rng.random() < 0.6:
+            blocks += dstar_slow_data_blocks(text=dstar_gga(lat=float(rng.uniform(0, 8959)), lon=float(rng.uniform(0, 17959)),
+                                                            south=bool(rng.integers(0, 2)), west=bool(rng.integers(0, 2))))
+        if rng.random() < 0.6:
+            blocks += dstar_slow_data_blocks(text=dstar_dprs("%s>API282,DSTAR*:!4807.03N/01131.00E>run %d" % (my, made)))
+        filler = bytes([0x66] * 6)
+        n_voice = int(rng.integers(25, 90))
+        halves = []
+        for b in blocks:
+            halves += [b[:3], b[3:]]
+        hi = 0
+        for k in range(n_voice):
+            voice = rng.integers(0, 2, size=72).astype(np.uint8)
+            sync_slot = (k % 21 == 0)
+            if sync_slot:
+                data = DSTAR_VOICE_SYNC
+            else:
+                h3 = halves[hi] if hi < len(halves) else filler[:3]
+                hi += 1
+                data = dstar_scramble(_lsb_bits(np.frombuffer(h3, dtype=np.uint8)))
+            out.append(np.concatenate([voice, data]))
+            made += 1
+        voice = rng.integers(0, 2, size=72).astype(np.uint8)
+        if rng.random() < 0.7:
+            out.append(np.concatenate([voice, DSTAR_TERMINATOR]))
+        else:
+            out.append(np.concatenate([voice, DSTAR_TERMINATOR[24:]]))
+        made += 1
+        out.append(rng.integers(0, 2, size=int(rng.integers(0, 600))).astype(np.uint8))
+    s = np.concatenate(out)
+    if bit_errors > 0:
+        s = (s ^ (rng.random(s.size) < bit_errors)).astype(np.uint8)
+    return s

@@ -149,6 +149,7 @@ typedef struct dh_decoder dh_decoder;
 #define DH_PROTO_YSF 1
 #define DH_PROTO_POCSAG 2
 #define DH_PROTO_NXDN 3   /* Digiham::Nxdn::Decoder, reference include/nxdn_decoder.hpp:9-14 */
+#define DH_PROTO_DSTAR 4  /* Digiham::DStar::Decoder, reference include/dstar_decoder.hpp:9-13 */
 
 DH_API int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto);
 /* Zero-copy input: device address (row of channel 0) and pitch where a producer such as dh_demod_process should

@@ -66,6 +66,8 @@ void decode_dmr(const uint8_t* sym, size_t n, int slotFilter, Decoded& out);
 void decode_ysf(const uint8_t* sym, size_t n, Decoded& out);
 void decode_pocsag(const uint8_t* sym, size_t n, Decoded& out);
 void decode_nxdn(const uint8_t* sym, size_t n, Decoded& out);
+void decode_dstar(const uint8_t* sym, size_t n, Decoded& out);
+int dstar_header_probe(const uint8_t* raw660, char* text, size_t cap);
 unsigned nxdn_viterbi(const uint8_t* packedDibits, unsigned nbits, uint8_t* out);
 int nxdn_sacch_probe(const uint8_t* dibits30, uint8_t out5[5]);
 int nxdn_facch1_probe(const uint8_t* dibits72);

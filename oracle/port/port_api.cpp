@@ -26,6 +26,7 @@ void decode(int proto, const uint8_t* sym, size_t n, int slotFilter, port::Decod
         case ORC_PROTO_YSF: port::decode_ysf(sym, n, d); break;
         case ORC_PROTO_POCSAG: port::decode_pocsag(sym, n, d); break;
         case ORC_PROTO_NXDN: port::decode_nxdn(sym, n, d); break;
+        case ORC_PROTO_DSTAR: port::decode_dstar(sym, n, d); break;
     }
 }
 
@@ -62,6 +63,9 @@ size_t orc_pipe(int proto, const float* in, size_t n, size_t, int slot_filter, u
     std::vector<uint8_t> sym;
     if (proto == ORC_PROTO_POCSAG) {
         port::Demod d(40, false, true);
+        d.run(in, n, sym);
+    } else if (proto == ORC_PROTO_DSTAR) {
+        port::Demod d(10, false, false);
         d.run(in, n, sym);
     } else {
         const bool nxdn = proto == ORC_PROTO_NXDN;
@@ -128,5 +132,6 @@ unsigned orc_hamming_distance(const uint8_t* a, const uint8_t* b, size_t n) { re
 unsigned orc_nxdn_trellis(const uint8_t* in, unsigned len, uint8_t* out) { return port::nxdn_viterbi(in, len, out); }
 int orc_nxdn_sacch(const uint8_t in[30], uint8_t out[5]) { return port::nxdn_sacch_probe(in, out); }
 int orc_nxdn_facch1(const uint8_t in[72]) { return port::nxdn_facch1_probe(in); }
+int orc_dstar_header(const uint8_t in[660], char* text, size_t cap) { return port::dstar_header_probe(in, text, cap); }
 
 }
