@@ -280,6 +280,26 @@ namespace Digiham {
 
     }
 
+    namespace Nxdn {
+
+        // reference include/nxdn_decoder.hpp:9-14
+        class Decoder: public Digiham::Decoder {
+            public:
+                Decoder(): Digiham::Decoder(DH_PROTO_NXDN, true) {}
+        };
+
+    }
+
+    namespace DStar {
+
+        // reference include/dstar_decoder.hpp:9-13
+        class Decoder: public Digiham::Decoder {
+            public:
+                Decoder(): Digiham::Decoder(DH_PROTO_DSTAR, true) {}
+        };
+
+    }
+
     namespace Pocsag {
 
         class Decoder: public Digiham::Decoder {

@@ -4,7 +4,7 @@
 // `while (module->canProcess()) module->process();`), chained through csdr ring buffers.
 // The csdr headers come from oracle/csdr_shim (libcsdr is not installed in this image); test code only.
 //
-// usage: facade_pipe <proto: dmr|ysf|pocsag|rrc|dvf> <in file> <out prefix>
+// usage: facade_pipe <proto: dmr|ysf|pocsag|nxdn|dstar|rrc|dvf> <in file> <out prefix>
 #include <csdr/ringbuffer.hpp>
 
 #include "rrc_filter.hpp"
@@ -14,6 +14,8 @@
 #include "dmr_decoder.hpp"
 #include "ysf_decoder.hpp"
 #include "pocsag_decoder.hpp"
+#include "nxdn_decoder.hpp"
+#include "dstar_decoder.hpp"
 #include "version.hpp"
 
 #include <cstdio>
@@ -95,13 +97,21 @@ int main(int argc, char** argv) {
             demod = new Digiham::Fsk::FskDemodulator(40, true);
             demod->setReader(new Csdr::RingbufferReader<float>(&in));
             dec = new Digiham::Pocsag::Decoder();
+        } else if (proto == "dstar") {
+            // examples/dstar-decoder.sh:19-21
+            demod = new Digiham::Fsk::FskDemodulator(10);
+            demod->setReader(new Csdr::RingbufferReader<float>(&in));
+            dec = new Digiham::DStar::Decoder();
         } else {
-            rrc = new Digiham::RrcFilter::WideRrcFilter();
+            const bool nxdn = proto == "nxdn";   // examples/nxdn48-decoder.sh:19-23: rrc_filter -n | gfsk -s 20
+            if (nxdn) rrc = new Digiham::RrcFilter::NarrowRrcFilter();
+            else rrc = new Digiham::RrcFilter::WideRrcFilter();
             rrc->setReader(new Csdr::RingbufferReader<float>(&in));
             rrc->setWriter(&filt);
-            demod = new Digiham::Fsk::GfskDemodulator(10);
+            demod = new Digiham::Fsk::GfskDemodulator(nxdn ? 20 : 10);
             demod->setReader(new Csdr::RingbufferReader<float>(&filt));
             if (proto == "dmr") dec = new Digiham::Dmr::Decoder();
+            else if (nxdn) dec = new Digiham::Nxdn::Decoder();
             else dec = new Digiham::Ysf::Decoder();
         }
         demod->setWriter(&syms);

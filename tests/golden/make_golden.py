@@ -1,5 +1,6 @@
 #!/usr/bin/env python3
-"""Regenerates tests/golden/golden_v1.npz from the COMPILED REFERENCE (oracle/_ref, built from the unmodified
+"""Regenerates tests/golden/golden_v1.npz (and golden_v2.npz: NXDN / D-Star; `make_golden.py v2` writes only that)
+from the COMPILED REFERENCE (oracle/_ref, built from the unmodified
 sources under /root/reference by oracle/Makefile).  Run where the reference tree exists:
 
     python tests/golden/make_golden.py
@@ -135,5 +136,89 @@ def main():
     print("wrote", path, os.path.getsize(path), "bytes,", len(g), "arrays")
 
 
+def main_v2():
+    """golden_v2.npz: NXDN and D-Star, same recipe as v1."""
+    ref = oracle_lib.ref()
+    assert ref is not None and ref.kind == "reference", "needs the compiled reference (make -C oracle ref)"
+    g = {}
+    rng = np.random.default_rng(20261018)
+    for k, err in enumerate([0.0, 0.01, 0.04]):
+        sym = synth.nxdn_symbols(60, seed=(404, 416, 420)[k], symbol_errors=err)
+        o, m = ref.decode(oracle_lib.PROTO_NXDN, sym)
+        g["nxdn%d_sym" % k] = sym
+        g["nxdn%d_out" % k] = o
+        g["nxdn%d_meta" % k] = np.frombuffer(m, dtype=np.uint8)
+    xs = synth.modulate(synth.nxdn_symbols(14, seed=410, lead_in=40), sps=20, snr_db=16, phase=7,
+                        rng=np.random.default_rng(5))
+    g["nxdn_pipe_in"] = xs
+    ps, po, pm = ref.pipe(oracle_lib.PROTO_NXDN, xs)
+    g["nxdn_pipe_sym"] = ps
+    g["nxdn_pipe_out"] = po
+    g["nxdn_pipe_meta"] = np.frombuffer(pm, dtype=np.uint8)
+    # Nxdn::Trellis on valid (punctured and clean) code sequences and on noise; SACCH / FACCH1 probes
+    for nbits in (72, 192):
+        packed = rng.integers(0, 256, size=(8, nbits // 8)).astype(np.uint8)
+        for r in range(5):
+            bits = np.concatenate([rng.integers(0, 2, nbits // 2 - 4), np.zeros(4, dtype=np.int64)]).astype(np.uint8)
+            enc = synth.ysf_conv_encode(bits)
+            coded = np.empty(nbits, dtype=np.uint8)
+            coded[0::2] = enc >> 1
+            coded[1::2] = enc & 1
+            if r >= 2:
+                coded[rng.choice(nbits, size=r, replace=False)] ^= 1
+            packed[r] = np.packbits(coded)
+        res = []
+        for r in range(8):
+            metric, out = ref.nxdn_trellis(packed[r], nbits)
+            res.append(np.concatenate([[metric], out]))
+        g["nxdn_trellis%d_in" % nbits] = packed
+        g["nxdn_trellis%d_out" % nbits] = np.stack(res).astype(np.uint8)
+    sac = np.stack([synth.nxdn_sacch_dibits(k % 4, 5 * k, rng.integers(0, 2, 18)) for k in range(12)])
+    sac[8:] ^= (rng.random(sac[8:].shape) < 0.1).astype(np.uint8) * 2
+    g["nxdn_sacch_in"] = sac
+    g["nxdn_sacch_out"] = np.stack([np.concatenate([[int(ref.nxdn_sacch(d)[0])], ref.nxdn_sacch(d)[1] * int(ref.nxdn_sacch(d)[0])])
+                                    for d in sac]).astype(np.uint8)
+    fac = []
+    for k in range(16):
+        d = (rng.random(80) < (0.1 if k % 2 else 0.5)).astype(np.uint8)
+        d[2:8] = synth._int_to_bits([0x08, 0x10, 0x01][k % 3], 6)
+        fac.append(synth.nxdn_facch1_dibits(d))
+    fac = np.stack(fac)
+    g["nxdn_facch1_in"] = fac
+    g["nxdn_facch1_out"] = np.array([ref.nxdn_facch1(d) for d in fac], dtype=np.int32)
+
+    for k, err in enumerate([0.0, 0.004, 0.02]):
+        sym = synth.dstar_symbols(260, seed=500 + k, bit_errors=err)
+        o, m = ref.decode(oracle_lib.PROTO_DSTAR, sym)
+        g["dstar%d_sym" % k] = sym
+        g["dstar%d_out" % k] = o
+        g["dstar%d_meta" % k] = np.frombuffer(m, dtype=np.uint8)
+    ds = np.concatenate([np.tile(np.array([1, 0], dtype=np.uint8), 150), synth.dstar_symbols(50, seed=510, lead_in=0)])
+    xd = synth.modulate(ds, sps=10, levels=synth.LEVELS2, snr_db=16, phase=3, rng=np.random.default_rng(6))
+    g["dstar_pipe_in"] = xd
+    ps, po, pm = ref.pipe(oracle_lib.PROTO_DSTAR, xd)
+    g["dstar_pipe_sym"] = ps
+    g["dstar_pipe_out"] = po
+    g["dstar_pipe_meta"] = np.frombuffer(pm, dtype=np.uint8)
+    hdrs, hres = [], []
+    for k in range(10):
+        hb = synth.dstar_header_bits(synth.dstar_header_bytes(flags=(0x80 if k == 3 else 0, 0, 0), my="GOLD%d" % k,
+                                                              suffix=["", "B200"][k % 2])).copy()
+        hb[rng.choice(660, size=[0, 2, 5, 9, 14, 20, 30, 45, 3, 7][k], replace=False)] ^= 1
+        rc, text = ref.dstar_header(hb)
+        hdrs.append(hb)
+        hres.append(np.frombuffer(("%d|" % rc).encode() + text + b"\0" * (128 - len(text) - len("%d|" % rc)), dtype=np.uint8))
+    g["dstar_header_in"] = np.stack(hdrs)
+    g["dstar_header_out"] = np.stack(hres)
+
+    path = os.path.join(HERE, "golden_v2.npz")
+    np.savez_compressed(path, **g)
+    print("wrote", path, os.path.getsize(path), "bytes,", len(g), "arrays")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "v2":
+        main_v2()
+    else:
+        main()
+        main_v2()

@@ -58,6 +58,24 @@ def test_facade_ysf_pipe(harness):
     assert out.size > 0 and b"mode:DN" in meta
 
 
+def test_facade_nxdn_pipe(harness):
+    sym = synth.nxdn_symbols(40, seed=8, lead_in=50)
+    x = synth.modulate(sym, sps=20, snr_db=18, rng=np.random.default_rng(1), phase=4)
+    out, meta = _run(harness, "nxdn", x)
+    _, ref_out, ref_meta = oracle_lib.best().pipe(oracle_lib.PROTO_NXDN, x, chunk=128)
+    assert np.array_equal(out, ref_out) and meta == ref_meta
+    assert out.size > 0 and b"protocol:NXDN;sync:voice" in meta
+
+
+def test_facade_dstar_pipe(harness):
+    sym = np.concatenate([np.tile(np.array([1, 0], dtype=np.uint8), 150), synth.dstar_symbols(80, seed=8, lead_in=0)])
+    x = synth.modulate(sym, sps=10, levels=synth.LEVELS2, snr_db=18, rng=np.random.default_rng(1), phase=4)
+    out, meta = _run(harness, "dstar", x)
+    _, ref_out, ref_meta = oracle_lib.best().pipe(oracle_lib.PROTO_DSTAR, x, chunk=128)
+    assert np.array_equal(out, ref_out) and meta == ref_meta
+    assert out.size > 0 and b"protocol:DSTAR" in meta
+
+
 def test_facade_pocsag_pipe(harness):
     bits = synth.pocsag_bits([(1234562, 3, "HELLO B200"), (42, 3, "FACADE")], seed=2, bit_errors=1)
     x = synth.modulate(bits, sps=40, levels=synth.LEVELS2[::-1].copy(), snr_db=20, rng=np.random.default_rng(3))

@@ -150,14 +150,14 @@ def _events(recs):
     return bytes(buf)
 
 
-def _replay(recs):
+def _replay(recs, proto=0):
     L = _lib()
     L.dh_meta_replay.argtypes = [ctypes.c_int, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_char_p, ctypes.c_size_t,
                                  ctypes.POINTER(ctypes.c_size_t)]
     ev = _events(recs)
     out = ctypes.create_string_buffer(1 << 16)
     n = ctypes.c_size_t()
-    assert L.dh_meta_replay(0, ev, len(recs), out, len(out), ctypes.byref(n)) == 0
+    assert L.dh_meta_replay(proto, ev, len(recs), out, len(out), ctypes.byref(n)) == 0
     return out.raw[:n.value].decode()
 
 
@@ -194,6 +194,52 @@ def test_dmr_meta_replay_talker_alias_and_gps():
     assert lines[1] == "protocol:DMR;slot:1;sync:voice;talkeralias:B200 TESTER"
     assert lines[2] == "lat:24.799994;lon:-12.799995;protocol:DMR;slot:1;sync:voice;talkeralias:B200 TESTER"
     assert lines[3] == ""     # after the collector reset a lone block 1 is incomplete -> no change
+
+
+def test_nxdn_meta_replay_lines():
+    """Host restatement of Nxdn::MetaCollector (reference src/nxdn_decoder/nxdn_meta.cpp:6-76): every setter sends
+    on its own, reset() batches, zero ids are not printed."""
+    lines = _replay([(1, 0, 0, 0, []),                          # setSync("voice")
+                     (1, 0, 0, 0, []),                          # unchanged
+                     (2, 0, 1, 0, [0x12, 0x34, 0xAB, 0xCD]),    # conference, source 4660, destination 43981
+                     (2, 0, 2, 0, [0x12, 0x34, 0x00, 0x00]),    # individual, destination 0 disappears
+                     (2, 0, 0, 0, [0x12, 0x34, 0x00, 0x00]),    # other call type: type removed
+                     (3, 0, 0, 0, []),
+                     (3, 0, 0, 0, [])], proto=3).split("\n")
+    assert lines == ["protocol:NXDN;sync:voice",
+                     "protocol:NXDN;sync:voice;type:conference",
+                     "protocol:NXDN;source:4660;sync:voice;type:conference",
+                     "destination:43981;protocol:NXDN;source:4660;sync:voice;type:conference",
+                     "destination:43981;protocol:NXDN;source:4660;sync:voice;type:individual",
+                     "protocol:NXDN;source:4660;sync:voice;type:individual",
+                     "protocol:NXDN;source:4660;sync:voice",
+                     "protocol:NXDN",
+                     ""]
+
+
+def test_dstar_meta_replay_lines():
+    """Host half of DStar::VoicePhase + MetaCollector (reference src/dstar_decoder/dstar_phase.cpp:151-278,
+    dstar_meta.cpp:5-130): header fields, 20-character message, header resend with CRC, DPRS and GGA sentences."""
+    from digiham_b200 import synth
+    hdr = bytes(synth.dstar_header_bytes(my="DL1ABC", suffix="B200", your="CQCQCQ"))
+    recs = [(1, 0, k, 0, hdr[12 * k:12 * k + 12]) for k in range(4)] + [(2, 0, 0, 0, [])]
+    recs += [(3, 0, 0, 0, b) for b in synth.dstar_slow_data_blocks(message="HELLO FROM B200")]
+    recs += [(4, 0, 1, 0, [])]
+    hdr2 = bytes(synth.dstar_header_bytes(my="W1AW", suffix="", your="DL1ABC"))
+    recs += [(3, 0, 0, 0, b) for b in synth.dstar_slow_data_blocks(header41=hdr2)]
+    recs += [(3, 0, 0, 0, b) for b in synth.dstar_slow_data_blocks(text=synth.dstar_gga(4807.038, 1131.0, False, True))]
+    recs += [(3, 0, 0, 0, b) for b in synth.dstar_slow_data_blocks(text=synth.dstar_dprs("X>Y:test"))]
+    recs += [(4, 0, 0, 0, []), (5, 0, 0, 0, [])]
+    lines = _replay(recs, proto=4).split("\n")
+    base = "departure:DB0XYZ B;destination:DB0XYZ G;"
+    assert lines[0] == base + "ourcall:DL1ABC/B200;protocol:DSTAR;sync:voice;yourcall:CQCQCQ"
+    assert lines[1] == base + "message:HELLO FROM B200     ;ourcall:DL1ABC/B200;protocol:DSTAR;sync:voice;yourcall:CQCQCQ"
+    assert lines[2] == base + "message:HELLO FROM B200     ;ourcall:W1AW;protocol:DSTAR;sync:voice;yourcall:DL1ABC"
+    assert lines[3] == base + ("lat:48.117302;lon:-11.516666;message:HELLO FROM B200     ;ourcall:W1AW;protocol:DSTAR;"
+                               "sync:voice;yourcall:DL1ABC")
+    assert lines[4] == base + ("dprs:X>Y:test;lat:48.117302;lon:-11.516666;message:HELLO FROM B200     ;ourcall:W1AW;"
+                               "protocol:DSTAR;sync:voice;yourcall:DL1ABC")
+    assert lines[5:] == ["protocol:DSTAR", ""]
 
 
 def test_synthetic_generators_are_deterministic():

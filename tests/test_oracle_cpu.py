@@ -9,6 +9,7 @@ import pytest
 import oracle_lib
 
 GOLDEN = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz"))
+GOLDEN2 = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_v2.npz"))   # NXDN / D-Star
 
 
 def _oracles():
@@ -137,6 +138,72 @@ def test_generated_luts_match_reference_for_every_syndrome():
             assert ok == bool(table[s, 0]), (name, s)
             if ok:
                 assert (s ^ lut[s]) == int(table[s, 1]), (name, s)
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_nxdn_golden(orc):
+    for k in range(3):
+        out, meta = orc.decode(oracle_lib.PROTO_NXDN, GOLDEN2["nxdn%d_sym" % k])
+        assert np.array_equal(out, GOLDEN2["nxdn%d_out" % k]), k
+        assert meta == GOLDEN2["nxdn%d_meta" % k].tobytes(), k
+    all_meta = b"".join(GOLDEN2["nxdn%d_meta" % k].tobytes() for k in range(3))
+    for key in (b"sync:voice", b"source:", b"destination:", b"type:"):
+        assert key in all_meta, key
+    sym, out, meta = orc.pipe(oracle_lib.PROTO_NXDN, GOLDEN2["nxdn_pipe_in"])
+    assert np.array_equal(sym, GOLDEN2["nxdn_pipe_sym"]) and np.array_equal(out, GOLDEN2["nxdn_pipe_out"])
+    assert meta == GOLDEN2["nxdn_pipe_meta"].tobytes() and out.size >= 18
+    for nbits in (72, 192):
+        for row, want in zip(GOLDEN2["nxdn_trellis%d_in" % nbits], GOLDEN2["nxdn_trellis%d_out" % nbits]):
+            metric, bits = orc.nxdn_trellis(row, nbits)
+            assert metric == want[0] and np.array_equal(bits, want[1:])
+    for d, want in zip(GOLDEN2["nxdn_sacch_in"], GOLDEN2["nxdn_sacch_out"]):
+        ok, data = orc.nxdn_sacch(d)
+        assert int(ok) == want[0] and (not ok or np.array_equal(data, want[1:]))
+    assert [orc.nxdn_facch1(d) for d in GOLDEN2["nxdn_facch1_in"]] == list(GOLDEN2["nxdn_facch1_out"])
+    assert 0x08 in GOLDEN2["nxdn_facch1_out"] and -1 in GOLDEN2["nxdn_facch1_out"]
+
+
+@pytest.mark.parametrize("orc", ORACLES, ids=IDS)
+def test_dstar_golden(orc):
+    for k in range(3):
+        out, meta = orc.decode(oracle_lib.PROTO_DSTAR, GOLDEN2["dstar%d_sym" % k])
+        assert np.array_equal(out, GOLDEN2["dstar%d_out" % k]), k
+        assert meta == GOLDEN2["dstar%d_meta" % k].tobytes(), k
+    all_meta = b"".join(GOLDEN2["dstar%d_meta" % k].tobytes() for k in range(3))
+    for key in (b"ourcall:", b"message:", b"lat:", b"dprs:"):
+        assert key in all_meta, key
+    sym, out, meta = orc.pipe(oracle_lib.PROTO_DSTAR, GOLDEN2["dstar_pipe_in"])
+    assert np.array_equal(sym, GOLDEN2["dstar_pipe_sym"]) and np.array_equal(out, GOLDEN2["dstar_pipe_out"])
+    assert meta == GOLDEN2["dstar_pipe_meta"].tobytes() and out.size >= 9
+    for bits, want in zip(GOLDEN2["dstar_header_in"], GOLDEN2["dstar_header_out"]):
+        rc, text = orc.dstar_header(bits)
+        assert ("%d|" % rc).encode() + text == want.tobytes().rstrip(b"\0")
+
+
+@pytest.mark.skipif(len(ORACLES) < 2, reason="needs both the compiled reference and the port")
+def test_port_equals_reference_nxdn_dstar():
+    ref, port = oracle_lib.ref(), oracle_lib.port()
+    from digiham_b200 import synth
+    rng = np.random.default_rng(6)
+    for k in range(6):
+        sym = synth.nxdn_symbols(80, seed=60 + k, symbol_errors=[0.0, 0.01, 0.05][k % 3])
+        a, b = ref.decode(oracle_lib.PROTO_NXDN, sym), port.decode(oracle_lib.PROTO_NXDN, sym)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], k
+        bits = synth.dstar_symbols(250, seed=70 + k, bit_errors=[0.0, 0.003, 0.03][k % 3])
+        a, b = ref.decode(oracle_lib.PROTO_DSTAR, bits), port.decode(oracle_lib.PROTO_DSTAR, bits)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1], k
+    noise4 = rng.integers(0, 4, 60000).astype(np.uint8)
+    for proto in (oracle_lib.PROTO_NXDN, oracle_lib.PROTO_DSTAR):
+        a, b = ref.decode(proto, noise4), port.decode(proto, noise4)
+        assert np.array_equal(a[0], b[0]) and a[1] == b[1]
+    for t in range(40):
+        nb = (72, 192)[t % 2]
+        d = rng.integers(0, 256, nb // 8).astype(np.uint8)
+        a, b = ref.nxdn_trellis(d, nb), port.nxdn_trellis(d, nb)
+        assert a[0] == b[0] and np.array_equal(a[1], b[1])
+    x = synth.modulate(synth.nxdn_symbols(30, seed=77), sps=20, snr_db=14, ppm=40, rng=np.random.default_rng(8))
+    a, b = ref.pipe(oracle_lib.PROTO_NXDN, x), port.pipe(oracle_lib.PROTO_NXDN, x)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
 
 
 @pytest.mark.skipif(len(ORACLES) < 2, reason="needs both the compiled reference and the port")
