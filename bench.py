@@ -126,6 +126,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-async", action="store_true",
+                    help="device arm: three kernels back to back on one stream instead of cross-step pipelining")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -180,9 +182,14 @@ def main():
 
     sampler = ClockSampler(local_rank)
     # ---- kernel-level arm: batch resident in HBM ---------------------------------------------------------------
+    # cross-step software pipelining (dh_pipe_set_async): K1 of step i+1 overlaps K2 + decoder of step i on two
+    # internal streams; every kernel of all K steps still runs inside the timed region (joined by pipe.sync)
+    pipe.set_async(not args.no_async)
+    config["pipelining"] = "none" if args.no_async else "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)"
     for _ in range(args.warmup):
         pipe.process(x, n=L)
-        pipe.decoder.discard()
+        pipe.discard()
+    pipe.sync()
     torch.cuda.synchronize()
     pipe.set_profiling(True)
     launches0 = pipe.launch_count
@@ -194,13 +201,15 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         pipe.process(x, n=L)
-        pipe.decoder.discard()       # results stay in HBM; only the device-side counters are reset
+        pipe.discard()               # results stay in HBM; only the device-side counters are reset
+    pipe.sync()                      # the timing stream waits for the last decoder kernel
     e1.record(stream)
     torch.cuda.synchronize()
     barrier()
     ms_total = e0.elapsed_time(e1)
     stage_ms, calls = pipe.stage_times()
     pipe.set_profiling(False)
+    pipe.set_async(False)
     launches = pipe.launch_count - launches0
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -316,8 +325,9 @@ def main():
                 "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / args.steps,
                                       "k3_k4_dmr": stage_ms[2] / args.steps,
                                       "launches_per_stage_per_step": calls / args.steps,
-                                      "note": "stages of consecutive sub-chunks overlap on two streams, so the "
-                                              "sum exceeds ms_per_step"},
+                                      "note": "per-kernel CUDA events on the launching streams; with cross-step "
+                                              "pipelining K1 of step i+1 runs beside K2/K3 of step i, so the sum "
+                                              "exceeds ms_per_step"},
                 "fp32_issue_bound": {"note": "K1 executes 162 separately rounded fp32 ops/sample (no FMA, bit-exact); "
                                              "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
                                      "fp32_ops_per_s": C * L * 162 / (k1_ms * 1e-3) if k1_ms > 0 else None,

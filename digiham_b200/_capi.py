@@ -90,6 +90,9 @@ def lib():
     L.dh_decoder_collect_results.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
     L.dh_pipe_set_sub_chunk.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
     L.dh_pipe_set_profiling.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dh_pipe_set_async.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    L.dh_pipe_sync.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_pipe_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_stage_times.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]
     L.dh_pipe_launch_count.argtypes = [ctypes.c_void_p]
     L.dh_pipe_launch_count.restype = ctypes.c_uint64
@@ -356,6 +359,16 @@ class Pipe:
 
     def set_profiling(self, enable):
         check(lib().dh_pipe_set_profiling(self._h, int(enable)))
+
+    def set_async(self, enable, stream=None):
+        """Cross-call software pipelining: K1 of call i+1 overlaps K2 + decoder of call i (join with sync())."""
+        check(lib().dh_pipe_set_async(self._h, int(enable), _stream_ptr(stream)))
+
+    def sync(self, stream=None):
+        check(lib().dh_pipe_sync(self._h, _stream_ptr(stream)))
+
+    def discard(self, stream=None):
+        check(lib().dh_pipe_discard(self._h, _stream_ptr(stream)))
 
     def stage_times(self):
         """([ms_rrc, ms_demod, ms_decoder] summed, calls) since the previous query (synchronises)."""

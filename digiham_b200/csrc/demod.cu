@@ -27,7 +27,9 @@
 namespace {
 
 constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (include/gfsk_demodulator.hpp:5-6)
-constexpr int kThreads = 64;   // 2 warps: 6 channels per CTA at sps = 10 (39 KB smem, 5 CTAs per SM)
+// 2 warps: 6 channels per CTA at sps = 10 (39 KB smem, 5 CTAs per SM).  4-warp CTAs (78 KB, 2 per SM) were measured
+// slower on B200 (0.42 vs 0.34 ms at 4096 channels: 342 CTAs are 1.15 waves of 2 x 148).
+constexpr int kThreads = 64;
 constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
 
 struct ChannelState {
@@ -168,8 +170,8 @@ __device__ __forceinline__ int processable(int T, int P, int vo, int sps) {
 }
 
 // SPS > 0: compile-time samples per symbol (fast path), SPS == 0: run-time p.sps
-template <int G, int SPS>
-__global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__ DemodParams p) {
+template <int G, int SPS, int THREADS>
+__global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ DemodParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kPerWarp = Group<G>::kPerWarp;
     constexpr int CH = Group<G>::kChunk;
@@ -179,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) demod_kernel(const __grid_constant__
     if (grp_in_warp >= kPerWarp) return;   // lanes that do not fill a whole group (30, 31 at G = 10)
     const int gl = lane - grp_in_warp * G;
     const int grp = warp * kPerWarp + grp_in_warp;
-    const int ch = blockIdx.x * ((kThreads / 32) * kPerWarp) + grp;
+    const int ch = blockIdx.x * ((THREADS / 32) * kPerWarp) + grp;
     if (ch >= p.channels) return;          // a whole group leaves together; shuffles below only name the own group
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
 
@@ -545,19 +547,23 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
 
     // lanes per channel: 10 on the sps = 10 fast path (3 channels per warp), else 16 or 32
     const int G = h->sps == 10 ? 10 : (h->sps <= 16 ? 16 : 32);
-    const int groups = (kThreads / 32) * (32 / G);
+    const int threads = kThreads;
+    const int groups = (threads / 32) * (32 / G);
     const unsigned grid = (h->channels + groups - 1) / groups;
     const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
+#define DH_LAUNCH_DEMOD(GG, SS, TT)                                                                                  \
+    do {                                                                                                             \
+        DH_CUDA(cudaFuncSetAttribute(demod_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        demod_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                          \
+    } while (0)
     if (G == 10) {
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<10, 10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        demod_kernel<10, 10><<<grid, kThreads, smem, st>>>(p);
+        DH_LAUNCH_DEMOD(10, 10, kThreads);
     } else if (G == 16) {
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        demod_kernel<16, 0><<<grid, kThreads, smem, st>>>(p);
+        DH_LAUNCH_DEMOD(16, 0, kThreads);
     } else {
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-        demod_kernel<32, 0><<<grid, kThreads, smem, st>>>(p);
+        DH_LAUNCH_DEMOD(32, 0, kThreads);
     }
+#undef DH_LAUNCH_DEMOD
     DH_CUDA(cudaGetLastError());
     h->cur ^= 1;   // the carried tails now sit in the other buffer
     return DH_OK;

@@ -50,6 +50,13 @@ struct dh_pipe {
     cudaStream_t sa = nullptr, sb = nullptr;
     cudaEvent_t ev_start = nullptr, ev_done = nullptr;
     std::vector<cudaEvent_t> ev_k1, ev_k2;
+    // Software pipelining ACROSS process calls (dh_pipe_set_async): K1 of call i+1 (stream a) overlaps K2 + decoder
+    // of call i (stream b).  The caller's stream only orders the input; results are joined by dh_pipe_sync /
+    // dh_pipe_collect.
+    bool async_mode = false;
+    uint64_t async_step = 0;
+    cudaEvent_t ev_a1[4] = {nullptr, nullptr, nullptr, nullptr}, ev_a2[4] = {nullptr, nullptr, nullptr, nullptr};
+    bool async_pending = false;        // work enqueued on the internal streams that `ev_done` covers
 };
 
 extern "C" {
@@ -158,6 +165,23 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
     if (n == 0) return DH_OK;
     cudaStream_t user = (cudaStream_t) stream;
     dh::DeviceGuard guard(h->device);
+    if (h->async_mode && h->rrc) {
+        // K1(i) may start as soon as the input is ready and K2(i - 2), the previous reader of the demodulator rows
+        // it alternates into, is done; K2(i) + decoder(i) follow on stream b
+        const uint64_t i = h->async_step++;
+        for (int k = 0; k < 4 && !h->ev_a1[3]; k++) {
+            DH_CUDA(cudaEventCreateWithFlags(&h->ev_a1[k], cudaEventDisableTiming));
+            DH_CUDA(cudaEventCreateWithFlags(&h->ev_a2[k], cudaEventDisableTiming));
+        }
+        DH_CUDA(cudaEventRecord(h->ev_start, user));
+        DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_start, 0));
+        if (i >= 2) DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_a2[(i - 2) & 3], 0));
+        int rc = run_stages(h, d_in, in_pitch, n, h->sa, h->sb, h->ev_a1[i & 3], h->ev_a2[i & 3]);
+        if (rc != DH_OK) return rc;
+        DH_CUDA(cudaEventRecord(h->ev_done, h->sb));
+        h->async_pending = true;
+        return DH_OK;
+    }
     if (!h->rrc || h->sub_chunk == 0 || n <= h->sub_chunk) return run_stages(h, d_in, in_pitch, n, user, user, nullptr, nullptr);
 
     // pipelined: K1(c) on stream a; K2(c) + decoder(c) on stream b after K1(c); K1(c) may only overwrite the
@@ -192,6 +216,32 @@ int dh_pipe_set_sub_chunk(dh_pipe* h, size_t sub_chunk) {
     DH_REQUIRE(sub_chunk % 4 == 0, DH_E_INVALID, "dh_pipe_set_sub_chunk: must be a multiple of 4");
     h->sub_chunk = sub_chunk;
     return DH_OK;
+}
+
+int dh_pipe_sync(dh_pipe* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_sync: handle is NULL");
+    if (!h->async_pending) return DH_OK;
+    dh::DeviceGuard guard(h->device);
+    // stream b runs the last stage of every call and waits for stream a's K1 of the same call
+    DH_CUDA(cudaStreamWaitEvent((cudaStream_t) stream, h->ev_done, 0));
+    h->async_pending = false;
+    return DH_OK;
+}
+
+int dh_pipe_set_async(dh_pipe* h, int enable, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_set_async: handle is NULL");
+    if (!enable) {
+        int rc = dh_pipe_sync(h, stream);
+        if (rc != DH_OK) return rc;
+    }
+    h->async_mode = enable != 0;
+    return DH_OK;
+}
+
+int dh_pipe_discard(dh_pipe* h, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_discard: handle is NULL");
+    // in asynchronous mode the counters belong to stream b (between the decoder kernels of consecutive calls)
+    return dh_decoder_discard(h->decoder, h->async_mode && h->rrc ? (void*) h->sb : stream);
 }
 
 int dh_pipe_set_profiling(dh_pipe* h, int enable) {
@@ -308,6 +358,8 @@ int dh_pipe_collect_step(dh_pipe* h) {
 
 int dh_pipe_collect(dh_pipe* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_collect: handle is NULL");
+    int rc = dh_pipe_sync(h, stream);
+    if (rc != DH_OK) return rc;
     return dh_decoder_collect(h->decoder, stream);
 }
 
@@ -324,6 +376,7 @@ int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, c
 int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t cap, size_t* count) {
     DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_pipe_read_symbols: bad handle or channel");
     dh::DeviceGuard guard(h->device);
+    if (h->async_pending) DH_CUDA(cudaStreamSynchronize(h->sb));
     uint32_t n = 0;
     DH_CUDA(cudaMemcpy(&n, h->d_nsym + channel, sizeof(n), cudaMemcpyDeviceToHost));
     if (count) *count = n;
@@ -343,6 +396,10 @@ void dh_pipe_destroy(dh_pipe* h) {
         for (cudaEvent_t e : h->events) cudaEventDestroy(e);
         for (cudaEvent_t e : h->ev_k1) cudaEventDestroy(e);
         for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);
+        for (int k = 0; k < 4; k++) {
+            if (h->ev_a1[k]) cudaEventDestroy(h->ev_a1[k]);
+            if (h->ev_a2[k]) cudaEventDestroy(h->ev_a2[k]);
+        }
         if (h->ev_start) cudaEventDestroy(h->ev_start);
         if (h->ev_done) cudaEventDestroy(h->ev_done);
         if (h->sa) cudaStreamDestroy(h->sa);

@@ -9,8 +9,9 @@
 // 2^32 float inputs, that fl32(fl64(s) * fl64(1/g)) == fl32(fl64(s) / g) for g in {8.337797030, 16.67711971}.
 //
 // Kernel shape (1-D convolution, FP32-issue bound at 2*(nZeros+1) flop per sample — no tensor cores):
-//   * one CTA = one (channel, time tile) of TILE = 128 threads x R outputs; R = 17 is odd so that the per-thread
-//     windows (stride R floats) fall into 32 different shared-memory banks without any padding;
+//   * one CTA = one (channel, time tile) of TILE = 128 threads x R outputs; R is odd (13..19, chosen per call so
+//     that the stream splits into equal tiles) so that the per-thread windows (stride R floats) fall into 32
+//     different shared-memory banks without any padding;
 //   * the tile and its nZeros-sample halo are brought in by TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) that
 //     signal an mbarrier; outputs leave through shared memory and one bulk store, so every HBM access is a
 //     full-line burst and the SM issue slots are left to FMUL/FADD;
@@ -28,8 +29,8 @@
 namespace {
 
 constexpr int kThreads = 128;
-constexpr int kR = 17;
-constexpr int kTile = kThreads * kR;  // 2176 outputs per CTA
+constexpr int kRDefault = 17;         // outputs per thread; odd, see the kernel comment
+constexpr int kMaxTile = kThreads * 19;
 constexpr int kMaxZeros = 1024;
 constexpr int kMaxTapsParam = 164;    // taps that travel in the kernel parameter (constant bank 0)
 
@@ -52,10 +53,29 @@ struct RrcParams {
     int pad_;
 };
 
+// Outputs per thread for a call of n samples.  A CTA slot costs the same whether its tile is full or ragged (the
+// surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..19 to
+// minimise tiles * (work per tile): e.g. n = 48000 -> R = 15, 25 full tiles instead of 22 + a ragged one at R = 17.
+inline int pick_r(size_t n, int nz) {
+    int best = kRDefault;
+    double best_cost = 1e300;
+    for (int r = 19; r >= 13; r -= 2) {
+        const size_t tiles = (n + (size_t) kThreads * r - 1) / ((size_t) kThreads * r);
+        // per tile and thread: (nz + 1) * (2 r + 2) issue slots + fixed prologue / epilogue
+        const double cost = (double) tiles * ((nz + 1) * (2.0 * r + 2.0) + 6.0 * r + 150.0);
+        if (cost < best_cost * 0.999) {
+            best_cost = cost;
+            best = r;
+        }
+    }
+    return best;
+}
+
 // NZ_CT > 0: compile-time tap count; RECIP: scale by the reciprocal gain (built-in filters) instead of dividing
-template <int NZ_CT, bool RECIP>
+template <int NZ_CT, bool RECIP, int kR>
 __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant__ RrcParams p,
                                                           const __grid_constant__ TapBlock taps) {
+    constexpr int kTile = kThreads * kR;
     extern __shared__ __align__(128) float s[];   // [nz + kTile] inputs, later reused for kTile outputs
     __shared__ __align__(8) uint64_t bar;
 
@@ -102,8 +122,11 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
 
     dh::mbar_wait(&bar, 0);
 
-    // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz
-    const int base = tid * kR;
+    // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz.
+    // The warps of a CTA always start on the same SM sub-partition, so the mapping warp -> part of the tile is
+    // rotated per channel: in a ragged last tile (see warp_live below) the surviving warps then spread over all
+    // four schedulers instead of piling up on the first one.
+    const int base = ((tid + 32 * (ch & 3)) & (kThreads - 1)) * kR;
     const float* sw = s + base;
     float acc[kR], w[kR];
 #pragma unroll
@@ -114,24 +137,26 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
 
     // a ragged last tile: warps whose outputs all lie beyond the end of the stream skip the arithmetic
     // (warp-uniform, so no divergence inside the FMUL/FADD stream)
-    const bool warp_live = (tid & ~31) * kR < valid;
-    const int ntaps = nz + 1;
-    const int full = warp_live ? ntaps / kR : 0;
-    int i0 = 0;
-#pragma unroll 1
-    for (int it = 0; it < full; it++, i0 += kR) {
-        const float* nxt = sw + i0 + kR;
-#pragma unroll
-        for (int k = 0; k < kR; k++) {
-            const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
-#pragma unroll
-            for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
-            // slot k held s[base + i0 + k] (the oldest sample, last used by r = 0); it now receives the
-            // sample that output r = kR-1 needs at the next tap.  Never read past tap index nz.
-            if (i0 + k < nz) w[k] = nxt[k];
-        }
-    }
+    const bool warp_live = (base / (32 * kR)) * (32 * kR) < valid;
     if (warp_live) {
+        const int ntaps = nz + 1;
+        const int full = ntaps / kR;   // compile-time for the built-in filters
+        int i0 = 0;
+        // rolled loop over groups of kR taps: ~10 KB of code.  Fully unrolling the 81-tap filter (45 KB, taps fetched
+        // by LDCU.128) was measured 9 % slower on B200 (instruction-cache misses).
+#pragma unroll 1
+        for (int it = 0; it < full; it++, i0 += kR) {
+            const float* nxt = sw + i0 + kR;
+#pragma unroll
+            for (int k = 0; k < kR; k++) {
+                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
+#pragma unroll
+                for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
+                // slot k held s[base + i0 + k] (the oldest sample, last used by r = 0); it now receives the
+                // sample that output r = kR-1 needs at the next tap.  Never read past tap index nz.
+                if (i0 + k < nz) w[k] = nxt[k];
+            }
+        }
         const int rem = ntaps - i0;   // < kR, identical for all threads
         const float* nxt = sw + i0 + kR;
 #pragma unroll
@@ -264,8 +289,10 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
     DH_REQUIRE(in_pitch % 4 == 0 && out_pitch % 4 == 0 && in_pitch >= n4 && out_pitch >= n4, DH_E_INVALID,
                "dh_rrc_process: pitches must be multiples of 4 and >= n rounded up to 4 (n=%zu in=%zu out=%zu)", n,
                in_pitch, out_pitch);
-    DH_REQUIRE(n <= 0x7fffffffu - kTile, DH_E_INVALID, "dh_rrc_process: n too large");
-    const size_t tiles = (n + kTile - 1) / kTile;
+    DH_REQUIRE(n <= 0x7fffffffu - kMaxTile, DH_E_INVALID, "dh_rrc_process: n too large");
+    const int r = pick_r(n, h->nz);
+    const size_t tile = (size_t) kThreads * r;
+    const size_t tiles = (n + tile - 1) / tile;
     DH_REQUIRE(tiles * h->channels <= 0x7fffffffu, DH_E_INVALID, "dh_rrc_process: channels x tiles too large");
 
     dh::DeviceGuard guard(h->device);
@@ -286,15 +313,22 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
 
     cudaStream_t st = (cudaStream_t) stream;
     const unsigned grid = (unsigned) (tiles * h->channels);
-    size_t smem = (size_t) (h->nz + kTile) * sizeof(float);
-    if (h->nz == 80 && h->mul_recip) {
-        rrc_fir_kernel<80, true><<<grid, kThreads, smem, st>>>(p, h->taps);
-    } else if (h->nz == 160 && h->mul_recip) {
-        rrc_fir_kernel<160, true><<<grid, kThreads, smem, st>>>(p, h->taps);
-    } else {
-        if (h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
-        rrc_fir_kernel<0, false><<<grid, kThreads, smem, st>>>(p, h->taps);
+    size_t smem = (size_t) (h->nz + tile) * sizeof(float);
+    const int which = h->nz == 80 && h->mul_recip ? 0 : (h->nz == 160 && h->mul_recip ? 1 : 2);
+    if (which == 2 && h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
+#define DH_LAUNCH_RRC(RR)                                                                       \
+    do {                                                                                        \
+        if (which == 0) rrc_fir_kernel<80, true, RR><<<grid, kThreads, smem, st>>>(p, h->taps);  \
+        else if (which == 1) rrc_fir_kernel<160, true, RR><<<grid, kThreads, smem, st>>>(p, h->taps); \
+        else rrc_fir_kernel<0, false, RR><<<grid, kThreads, smem, st>>>(p, h->taps);             \
+    } while (0)
+    switch (r) {
+        case 13: DH_LAUNCH_RRC(13); break;
+        case 15: DH_LAUNCH_RRC(15); break;
+        case 19: DH_LAUNCH_RRC(19); break;
+        default: DH_LAUNCH_RRC(17); break;
     }
+#undef DH_LAUNCH_RRC
     DH_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return DH_OK;

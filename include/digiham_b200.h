@@ -233,6 +233,17 @@ DH_API int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_p
  * caller's stream is joined before the call returns control of it.  0 (the default) runs the three kernels back to
  * back on the caller's stream.  Results are identical either way. */
 DH_API int dh_pipe_set_sub_chunk(dh_pipe* h, size_t sub_chunk);
+/* Software pipelining ACROSS dh_pipe_process_device calls (off by default).  When enabled, a call only orders
+ * itself after the work already enqueued on `stream` (the producer of d_in) and returns with its three kernels
+ * enqueued on internal streams: the RRC kernel of call i+1 overlaps the demodulator + decoder kernels of call i
+ * (the FIR is issue-bound, the other two are latency-bound walks).  Results are bit-identical.  The caller joins
+ * with dh_pipe_sync (makes `stream` wait for everything enqueued so far; also required before d_in is
+ * overwritten) or dh_pipe_collect (which syncs first); dh_pipe_discard drops device-side results in pipeline
+ * order.  In the reference the same overlap exists between the processes of a shell pipe
+ * (examples/dmr-decoder.sh:19-23). */
+DH_API int dh_pipe_set_async(dh_pipe* h, int enable, void* stream);
+DH_API int dh_pipe_sync(dh_pipe* h, void* stream);
+DH_API int dh_pipe_discard(dh_pipe* h, void* stream);
 /* Per-stage device timing: when enabled every process call records CUDA events on the caller's stream around
  * K1 (RRC), K2 (demodulator) and the decoder kernel, each on the stream the kernel runs on.
  * dh_pipe_stage_times waits for the recorded work, returns the summed milliseconds per stage since the previous

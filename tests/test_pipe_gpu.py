@@ -113,6 +113,30 @@ def test_pipe_streaming_submit_equals_blocking_calls():
     pipe.close()
 
 
+def test_pipe_async_pipelining_equals_blocking_calls():
+    """dh_pipe_set_async: K1 of call i+1 overlaps K2 + decoder of call i on internal streams; the streams carry the
+    same dependencies as the single-stream order, so the results are identical (checked against the oracle)."""
+    import digiham_b200 as dh
+    C, n, chunk = 256, 96000, 12000
+    x, _ = synth.dmr_channel_bank(C, n, seed=17, device="cuda")
+    pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=chunk)
+    pipe.set_async(True)
+    for k, pos in enumerate(range(0, n, chunk)):
+        pipe.process(x[:, pos:pos + chunk], n=chunk)
+        if k % 2 == 1:
+            pipe.collect()           # syncs, reads back (result buffers hold two calls)
+    pipe.collect()
+    pipe.set_async(False)
+    orc = oracle_lib.best()
+    _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, x[:, :n].cpu().numpy(), threads=8)
+    total = 0
+    for ch in range(C):
+        assert pipe.output(ch) == outs[ch].tobytes() and pipe.meta(ch) == metas[ch], ch
+        total += len(outs[ch])
+    assert total > 27 * 200
+    pipe.close()
+
+
 def test_pipe_full_size_properties():
     """4096 channels (BASELINE config 2): results must not depend on the chunking, and duplicated channels must
     produce identical streams (no cross-channel interference)."""
