@@ -208,8 +208,15 @@ def main():
     barrier()
     ms_total = e0.elapsed_time(e1)
     stage_ms, calls = pipe.stage_times()
-    pipe.set_profiling(False)
     pipe.set_async(False)
+    # the same kernels once more WITHOUT cross-step overlap (outside the timed region): K1's launch time with the
+    # SMs to itself, reported beside the in-region figure
+    iso_steps = 0 if args.no_async else min(10, args.steps)
+    for _ in range(iso_steps):
+        pipe.process(x, n=L)
+        pipe.discard()
+    iso_ms, iso_calls = pipe.stage_times() if iso_steps else ([0.0, 0.0, 0.0], 0)
+    pipe.set_profiling(False)
     launches = pipe.launch_count - launches0
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -318,8 +325,18 @@ def main():
             tj = json.load(f)
         if tj.get("channels") == C and tj.get("samples") == L:
             traffic = tj.get("dram_bytes_per_launch")
+    iso = None
+    if iso_calls:
+        iso_k1 = iso_ms[0] / iso_calls
+        iso_ach = C * L * ALGO_BYTES_PER_SAMPLE_K1 / (iso_k1 * 1e-3) / 1e9
+        iso = {"ms_per_launch": iso_k1, "achieved": iso_ach, "frac": iso_ach / peak, "launches": iso_calls,
+               "stage_ms_per_step": {"k1_rrc": iso_k1, "k2_demod": iso_ms[1] / iso_calls, "k3_k4_dmr": iso_ms[2] / iso_calls},
+               "note": "same kernels, same inputs, three kernels back to back on one stream right after the timed "
+                       "region: K1 with the SMs to itself.  In the timed region K1 of step i+1 shares the SMs with K2/K3 "
+                       "of step i, which stretches its launch duration while shortening the step"}
     roofline = {"bound": "hbm", "kernel": "rrc_fir_kernel<80> (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+                "not_overlapped": iso,
                 "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_K1,
                 "ms_per_launch": k1_ms * args.steps / max(1, calls), "k1_ms_per_step": k1_ms,
                 "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / args.steps,
