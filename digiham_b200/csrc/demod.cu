@@ -387,6 +387,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
         // load->store round trip per element
         const float* src = row + col0 + P;
         float* dst = p.work_next + (size_t) ch * p.pitch + p.carry_cap - keep;
+        __syncwarp(gmask);   // every lane of the group is done reading the staged block (window sums of a partial block)
         for (int idx = gl; idx < keep; idx += G) cp_async4(S + idx, src + idx);
         cp_async_commit();
         cp_async_wait_all();
@@ -425,9 +426,12 @@ int demod_reserve(dh_demod* h, size_t max_n) {
     const size_t n4 = (max_n + 3) & ~(size_t) 3;
     const size_t pitch = (size_t) h->carry_cap + n4;
     float* nw[2] = {nullptr, nullptr};
+    // + one 16-byte vector: the staging copies of the kernel are whole float4s and the range they cover may end one
+    // sample past the last row (a block staged with a pending -1 nudge)
+    const size_t alloc_bytes = ((size_t) h->channels * pitch + 4) * sizeof(float);
     for (int b = 0; b < 2; b++) {
-        DH_CUDA(cudaMalloc(&nw[b], (size_t) h->channels * pitch * sizeof(float)));
-        DH_CUDA(cudaMemset(nw[b], 0, (size_t) h->channels * pitch * sizeof(float)));
+        DH_CUDA(cudaMalloc(&nw[b], alloc_bytes));
+        DH_CUDA(cudaMemset(nw[b], 0, alloc_bytes));
     }
     if (h->d_work[0]) {
         // keep the carried tails (they live in the buffer the next call reads); the bank may be mid-stream

@@ -11,6 +11,7 @@
 // input rows (dh_demod_reserve / dh_decoder_reserve), so no intermediate copy exists.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <new>
 #include <vector>
 
@@ -57,6 +58,7 @@ struct dh_pipe {
     uint64_t async_step = 0;
     cudaEvent_t ev_a1[4] = {nullptr, nullptr, nullptr, nullptr}, ev_a2[4] = {nullptr, nullptr, nullptr, nullptr};
     bool async_pending = false;        // work enqueued on the internal streams that `ev_done` covers
+    cudaEvent_t ev_last_k1 = nullptr;  // K1 of the most recent asynchronous call (the last reader of its input)
 };
 
 extern "C" {
@@ -93,8 +95,13 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
         dh::DeviceGuard guard(device);
         int lo_prio = 0, hi_prio = 0;
         cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
-        cudaError_t e = cudaStreamCreateWithPriority(&h->sa, cudaStreamNonBlocking, lo_prio);
-        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, hi_prio);
+        int pa = lo_prio, pb = hi_prio;
+        if (const char* env = getenv("DH_PIPE_PRIO")) {   // experiment switch
+            if (atoi(env) == 1) pa = pb = lo_prio;
+            if (atoi(env) == 2) { pa = hi_prio; pb = lo_prio; }
+        }
+        cudaError_t e = cudaStreamCreateWithPriority(&h->sa, cudaStreamNonBlocking, pa);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->sb, cudaStreamNonBlocking, pb);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaMalloc(&h->d_nsym, (size_t) channels * sizeof(uint32_t));
@@ -180,6 +187,7 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
         if (rc != DH_OK) return rc;
         DH_CUDA(cudaEventRecord(h->ev_done, h->sb));
         h->async_pending = true;
+        h->ev_last_k1 = h->ev_a1[i & 3];
         return DH_OK;
     }
     if (!h->rrc || h->sub_chunk == 0 || n <= h->sub_chunk) return run_stages(h, d_in, in_pitch, n, user, user, nullptr, nullptr);
@@ -284,6 +292,8 @@ int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t 
         DH_CUDA(cudaMemset(h->d_stage, 0, (size_t) h->channels * h->stage_pitch * sizeof(float)));
     }
     cudaStream_t st = (cudaStream_t) stream;
+    // asynchronous mode: the staging block is still being read by K1 of the previous call (internal stream)
+    if (h->async_pending && h->ev_last_k1) DH_CUDA(cudaStreamWaitEvent(st, h->ev_last_k1, 0));
     if (in_pitch == h->stage_pitch) {
         // one contiguous transfer
         DH_CUDA(cudaMemcpyAsync(h->d_stage, h_in, (size_t) h->channels * in_pitch * sizeof(float),

@@ -137,6 +137,29 @@ def test_pipe_async_pipelining_equals_blocking_calls():
     pipe.close()
 
 
+def test_pipe_async_host_input():
+    """asynchronous mode with HOST input: the staging copy of call i+1 must wait for K1 of call i"""
+    import digiham_b200 as dh
+    C, n, chunk = 64, 60000, 6000
+    x, _ = synth.dmr_channel_bank(C, n, seed=19, device="cpu")
+    pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=chunk)
+    pipe.set_async(True)
+    blocks = []
+    for pos in range(0, n, chunk):
+        b = torch.zeros((C, pipe.host_pitch), dtype=torch.float32).pin_memory()
+        b[:, :chunk] = x[:, pos:pos + chunk]
+        blocks.append(b)
+    for k, b in enumerate(blocks):
+        pipe.process(b, n=chunk)
+        if k % 2 == 1:
+            pipe.collect()
+    pipe.collect()
+    _, outs, metas = oracle_lib.best().pipe_batch(oracle_lib.PROTO_DMR, x[:, :n].numpy(), threads=8)
+    for ch in range(C):
+        assert pipe.output(ch) == outs[ch].tobytes() and pipe.meta(ch) == metas[ch], ch
+    pipe.close()
+
+
 def test_pipe_full_size_properties():
     """4096 channels (BASELINE config 2): results must not depend on the chunking, and duplicated channels must
     produce identical streams (no cross-channel interference)."""
