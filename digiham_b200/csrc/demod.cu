@@ -62,8 +62,8 @@ struct DemodParams {
 __device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
 __device__ __forceinline__ float max_gt(float cur, float v) { return v > cur ? v : cur; }
 
-// x / c for the divisors of the sps = 10 fast path, as fl32(fl64(x) * fl64(1/c)): bit-identical to the float
-// division for EVERY finite float x when c is 10 or 100 (exhaustive proof: tests/test_host_logic.py::
+// x / c for the divisors of the fast paths, as fl32(fl64(x) * fl64(1/c)): bit-identical to the float division for
+// EVERY float x when c is 6, 10, 14, 20, 40 or 100 (exhaustive proof: tests/test_host_logic.py::
 // test_division_by_constant_exhaustive), and three instructions instead of the IEEE division sequence.
 __device__ __forceinline__ float div_by_const(float x, double reciprocal) {
     return __double2float_rn(__dmul_rn((double) x, reciprocal));
@@ -169,7 +169,12 @@ __device__ __forceinline__ int processable(int T, int P, int vo, int sps) {
     return 1 + (room >= sps ? min(kBlockSyms - 1, room / sps) : 0);
 }
 
-// SPS > 0: compile-time samples per symbol (fast path), SPS == 0: run-time p.sps
+// SPS > 0: compile-time samples per symbol (fast paths for 10, 20 and 40 = DMR/YSF/D-Star, NXDN, POCSAG at 48 kHz:
+// unrolled windows, evaluation window lo/hi as constants, divisions by sps, hi - lo and 100 as reciprocal
+// multiplications proven exact for every float), SPS == 0: run-time p.sps
+__host__ __device__ constexpr int eval_lo(int sps) { return (2 * sps + 3) / 6; }   // == roundf(sps / 3.0f) for 10, 20, 40 (checked by the host)
+__host__ __device__ constexpr int eval_hi(int sps) { return (4 * sps + 3) / 6; }   // == roundf(sps * 2 / 3.0f)
+
 template <int G, int SPS, int THREADS>
 __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ DemodParams p) {
     extern __shared__ __align__(16) float smem[];
@@ -186,8 +191,8 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
 
     const int sps = SPS > 0 ? SPS : p.sps;
-    const int lo = SPS == 10 ? 3 : p.lo;
-    const int hi = SPS == 10 ? 7 : p.hi;
+    const int lo = SPS > 0 ? eval_lo(SPS) : p.lo;
+    const int hi = SPS > 0 ? eval_hi(SPS) : p.hi;
     float* S = smem + (size_t) grp * p.group_floats;                 // staged samples of the current block
     double* var = reinterpret_cast<double*>(S + p.samples_cap);     // [sps] phase variances
 
@@ -239,15 +244,17 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
             if (j < m) {
                 const float* w = S + a0 + j * sps + (j ? vo : 0);
                 float sum = 0.0f, vsum = 0.0f;
-                if (SPS == 10) {
+                if (SPS > 0) {
+                    constexpr int kLo = eval_lo(SPS > 0 ? SPS : 10), kHi = eval_hi(SPS > 0 ? SPS : 10);
 #pragma unroll
-                    for (int i = 0; i < 10; i++) {
+                    for (int i = 0; i < SPS; i++) {
                         const float v = w[i];
-                        if (i >= 3 && i < 7) sum = __fadd_rn(sum, v);
+                        if (i >= kLo && i < kHi) sum = __fadd_rn(sum, v);
                         vsum = __fadd_rn(vsum, v);
                     }
-                    volr[q] = div_by_const(vsum, 1.0 / 10.0);
-                    avgr[q] = __fmul_rn(sum, 0.25f);   // / 4.0f, exact scaling
+                    volr[q] = div_by_const(vsum, 1.0 / (double) (SPS > 0 ? SPS : 1));
+                    avgr[q] = kHi - kLo == 4 ? __fmul_rn(sum, 0.25f)   // / 4.0f, exact scaling
+                                             : div_by_const(sum, 1.0 / (double) (kHi - kLo));
                 } else {
                     for (int i = 0; i < sps; i++) {
                         const float v = w[i];
@@ -268,19 +275,19 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
                 const float* w0 = S + a0 + i;
                 const float* wv = w0 + vo;          // windows 1..99 are shifted by the pending nudge
                 float total = __fadd_rn(0.0f, w0[0]);
-                if (SPS == 10) {
+                if (SPS > 0) {
 #pragma unroll 11
-                    for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * 10]);
+                    for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * SPS]);
                 } else {
                     for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * sps]);
                 }
-                const double mean = (double) (SPS == 10 ? div_by_const(total, 1.0 / 100.0) : __fdiv_rn(total, 100.0f));
+                const double mean = (double) (SPS > 0 ? div_by_const(total, 1.0 / 100.0) : __fdiv_rn(total, 100.0f));
                 double d = __dsub_rn(mean, (double) w0[0]);
                 double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
-                if (SPS == 10) {
+                if (SPS > 0) {
 #pragma unroll 11
                     for (int k = 1; k < kBlockSyms; k++) {
-                        d = __dsub_rn(mean, (double) wv[k * 10]);
+                        d = __dsub_rn(mean, (double) wv[k * SPS]);
                         dsum = __dadd_rn(dsum, __dmul_rn(d, d));
                     }
                 } else {
@@ -549,9 +556,10 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     // samples | var (doubles; 8-byte aligned because samples_cap is a multiple of 4)
     p.group_floats = p.samples_cap + 2 * ((h->sps + 1) & ~1);
 
-    // lanes per channel: 10 on the sps = 10 fast path (3 channels per warp), else 16 or 32
-    const int G = h->sps == 10 ? 10 : (h->sps <= 16 ? 16 : 32);
-    const int threads = kThreads;
+    // lanes per channel: 10 on the compile-time fast paths (3 channels per warp), else 16 or 32
+    const bool fast = (h->sps == 10 || h->sps == 20 || h->sps == 40) && h->lo == eval_lo(h->sps) && h->hi == eval_hi(h->sps);
+    const int G = fast ? 10 : (h->sps <= 16 ? 16 : 32);
+    const int threads = fast && h->sps == 40 ? 32 : kThreads;
     const int groups = (threads / 32) * (32 / G);
     const unsigned grid = (h->channels + groups - 1) / groups;
     const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
@@ -560,8 +568,12 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         DH_CUDA(cudaFuncSetAttribute(demod_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
         demod_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                          \
     } while (0)
-    if (G == 10) {
+    if (G == 10 && h->sps == 10) {
         DH_LAUNCH_DEMOD(10, 10, kThreads);
+    } else if (G == 10 && h->sps == 20) {
+        DH_LAUNCH_DEMOD(10, 20, kThreads);
+    } else if (G == 10) {
+        DH_LAUNCH_DEMOD(10, 40, 32);   // 16 KB of staged samples per channel: one warp (3 channels) per CTA
     } else if (G == 16) {
         DH_LAUNCH_DEMOD(16, 0, kThreads);
     } else {

@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "tables.inc"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -57,6 +58,10 @@ struct RrcParams {
 // surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..19 to
 // minimise tiles * (work per tile): e.g. n = 48000 -> R = 15, 25 full tiles instead of 22 + a ragged one at R = 17.
 inline int pick_r(size_t n, int nz) {
+    if (const char* env = getenv("DH_RRC_R")) {   // experiment switch
+        const int r = atoi(env);
+        if (r == 13 || r == 15 || r == 17 || r == 19) return r;
+    }
     int best = kRDefault;
     double best_cost = 1e300;
     for (int r = 19; r >= 13; r -= 2) {

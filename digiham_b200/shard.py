@@ -46,15 +46,20 @@ def scatter_channels(x_full, channels, pitch, dtype=torch.float32, src=0, device
 
 
 def pack_rows(items, width=None, device="cpu"):
-    """list of bytes objects -> (uint8 tensor [n, width], int32 lengths)."""
-    lens = torch.tensor([len(b) for b in items], dtype=torch.int32)
+    """list of bytes objects -> (uint8 tensor [n, width], int32 lengths); vectorised (no per-row Python work)."""
+    import numpy as np
+    lens_np = np.fromiter((len(b) for b in items), dtype=np.int64, count=len(items))
     if width is None:
-        width = int(lens.max().item()) if len(items) else 0
-    buf = torch.zeros((len(items), max(1, width)), dtype=torch.uint8)
-    for i, b in enumerate(items):
-        if len(b):
-            buf[i, :len(b)] = torch.frombuffer(bytearray(b), dtype=torch.uint8)
-    return buf.to(device), lens.to(device)
+        width = int(lens_np.max()) if len(items) else 0
+    buf = np.zeros((len(items), max(1, width)), dtype=np.uint8)
+    total = int(lens_np.sum())
+    if total:
+        flat = np.frombuffer(b"".join(bytes(b) for b in items), dtype=np.uint8)
+        starts = np.cumsum(lens_np) - lens_np
+        rows = np.repeat(np.arange(len(items)), lens_np)
+        cols = np.arange(total) - np.repeat(starts, lens_np)
+        buf[rows, cols] = flat
+    return torch.from_numpy(buf).to(device), torch.from_numpy(lens_np.astype(np.int32)).to(device)
 
 
 def gather_frames(local_items, channels, dst=0, device="cpu"):
@@ -78,7 +83,8 @@ def gather_frames(local_items, channels, dst=0, device="cpu"):
     out = []
     for r in range(world):
         a, b = channel_range(r, world, channels)
-        rb, rl = bufs[r].cpu(), lenss[r].cpu()
-        for i in range(b - a):
-            out.append(bytes(rb[i, :int(rl[i])].numpy().tobytes()))
+        rb, rl = bufs[r].cpu().numpy(), lenss[r].cpu().numpy()
+        raw = rb.tobytes()
+        w = rb.shape[1]
+        out.extend(raw[i * w:i * w + int(rl[i])] for i in range(b - a))
     return out

@@ -106,9 +106,9 @@ DIVC_SRC = r"""
 #include <string.h>
 #include <math.h>
 int main(void) {
-    const float cs[2] = {10.0f, 100.0f};
+    const float cs[6] = {10.0f, 100.0f, 20.0f, 40.0f, 6.0f, 14.0f};   /* sps, 100, and hi - lo of the fast paths */
     unsigned long long bad = 0;
-    for (int g = 0; g < 2; g++) {
+    for (int g = 0; g < 6; g++) {
         const float c = cs[g];
         const double rc = 1.0 / (double) c;
         #pragma omp parallel for reduction(+:bad) schedule(static)
@@ -129,7 +129,7 @@ int main(void) {
 
 
 def test_division_by_constant_exhaustive():
-    """K2's sps = 10 path computes x / 10 and x / 100 as fl32(fl64(x) * fl64(1/c)); identical to the float division
+    """K2's fast paths (sps 10, 20, 40) compute x / sps, x / (hi - lo) and x / 100 as fl32(fl64(x) * fl64(1/c)); identical to the float division
     of the reference (gfsk_demodulator.cpp:53,82) for EVERY float32 x (DH_FAST_TESTS=1 samples every 7th)."""
     stride = 7 if os.environ.get("DH_FAST_TESTS") else 1
     with tempfile.TemporaryDirectory() as d:
