@@ -107,6 +107,34 @@ def reference_arm(args, x_host_rows, cores):
     return nch * n / sec / 1e6, orc.kind, "%d channels x %d samples per step, %d step(s)" % (nch, n, len(times)), sec
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """N > 1: keep this rank (and the pinned host blocks it allocates) on the NUMA node of its GPU, so that the
+    per-GPU PCIe uploads of the e2e arm do not cross the socket interconnect.  Best effort; returns a description."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus.lower()[-12:]
+        if not os.path.exists(path):
+            path = "/sys/bus/pci/devices/%s/local_cpulist" % bus.lower()
+        cpus = set()
+        for part in open(path).read().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return "%d cpus local to %s" % (len(allowed), bus)
+        return "no local cpu in the allowed set"
+    except Exception as ex:   # affinity is an optimisation, never a requirement
+        return "unavailable (%s)" % type(ex).__name__
+
+
 def build_host_sample(channels, n, seed):
     """CPU-side generation of a bounded sample of the workload (used by --impl reference on a box whose GPU arm
     is not running): same generator, same seed, first `channels` channels."""
@@ -168,6 +196,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        config["numa"] = bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 

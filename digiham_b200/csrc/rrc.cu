@@ -22,6 +22,7 @@
 #include "common.cuh"
 #include "tables.inc"
 
+#include <algorithm>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -85,8 +86,8 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
     __shared__ __align__(8) uint64_t bar;
 
     const int nz = NZ_CT > 0 ? NZ_CT : p.nz;
-    const int tile = blockIdx.x % p.tiles;
-    const int ch = blockIdx.x / p.tiles;
+    const int tile = blockIdx.x;   // 2-D grid (tiles, channels): no integer division in the prologue
+    const int ch = blockIdx.y;
     const int t0 = tile * kTile;
     const int valid = min(kTile, p.n - t0);
     const float* in_row = p.in + (size_t) ch * p.in_pitch;
@@ -127,11 +128,8 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
 
     dh::mbar_wait(&bar, 0);
 
-    // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz.
-    // The warps of a CTA always start on the same SM sub-partition, so the mapping warp -> part of the tile is
-    // rotated per channel: in a ragged last tile (see warp_live below) the surviving warps then spread over all
-    // four schedulers instead of piling up on the first one.
-    const int base = ((tid + 32 * (ch & 3)) & (kThreads - 1)) * kR;
+    // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz
+    const int base = tid * kR;
     const float* sw = s + base;
     float acc[kR], w[kR];
 #pragma unroll
@@ -142,7 +140,7 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
 
     // a ragged last tile: warps whose outputs all lie beyond the end of the stream skip the arithmetic
     // (warp-uniform, so no divergence inside the FMUL/FADD stream)
-    const bool warp_live = (base / (32 * kR)) * (32 * kR) < valid;
+    const bool warp_live = (tid & ~31) * kR < valid;
     if (warp_live) {
         const int ntaps = nz + 1;
         const int full = ntaps / kR;   // compile-time for the built-in filters
@@ -298,7 +296,7 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
     const int r = pick_r(n, h->nz);
     const size_t tile = (size_t) kThreads * r;
     const size_t tiles = (n + tile - 1) / tile;
-    DH_REQUIRE(tiles * h->channels <= 0x7fffffffu, DH_E_INVALID, "dh_rrc_process: channels x tiles too large");
+    DH_REQUIRE(tiles <= 0x7fffffffu, DH_E_INVALID, "dh_rrc_process: too many tiles");
 
     dh::DeviceGuard guard(h->device);
     RrcParams p;
@@ -317,21 +315,30 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
     p.pad_ = 0;
 
     cudaStream_t st = (cudaStream_t) stream;
-    const unsigned grid = (unsigned) (tiles * h->channels);
     size_t smem = (size_t) (h->nz + tile) * sizeof(float);
     const int which = h->nz == 80 && h->mul_recip ? 0 : (h->nz == 160 && h->mul_recip ? 1 : 2);
     if (which == 2 && h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
 #define DH_LAUNCH_RRC(RR)                                                                       \
     do {                                                                                        \
-        if (which == 0) rrc_fir_kernel<80, true, RR><<<grid, kThreads, smem, st>>>(p, h->taps);  \
-        else if (which == 1) rrc_fir_kernel<160, true, RR><<<grid, kThreads, smem, st>>>(p, h->taps); \
-        else rrc_fir_kernel<0, false, RR><<<grid, kThreads, smem, st>>>(p, h->taps);             \
+        if (which == 0) rrc_fir_kernel<80, true, RR><<<grid, kThreads, smem, st>>>(q, h->taps);  \
+        else if (which == 1) rrc_fir_kernel<160, true, RR><<<grid, kThreads, smem, st>>>(q, h->taps); \
+        else rrc_fir_kernel<0, false, RR><<<grid, kThreads, smem, st>>>(q, h->taps);             \
     } while (0)
-    switch (r) {
-        case 13: DH_LAUNCH_RRC(13); break;
-        case 15: DH_LAUNCH_RRC(15); break;
-        case 19: DH_LAUNCH_RRC(19); break;
-        default: DH_LAUNCH_RRC(17); break;
+    // grid = (tiles, channels); grid.y is limited to 65535, larger banks are launched in channel slices
+    for (size_t c0 = 0; c0 < h->channels; c0 += 65535) {
+        const size_t cnt = std::min<size_t>(65535, h->channels - c0);
+        RrcParams q = p;
+        q.in += c0 * in_pitch;
+        q.out += c0 * out_pitch;
+        q.hist_in += c0 * h->nz;
+        q.hist_out += c0 * h->nz;
+        const dim3 grid((unsigned) tiles, (unsigned) cnt, 1);
+        switch (r) {
+            case 13: DH_LAUNCH_RRC(13); break;
+            case 15: DH_LAUNCH_RRC(15); break;
+            case 19: DH_LAUNCH_RRC(19); break;
+            default: DH_LAUNCH_RRC(17); break;
+        }
     }
 #undef DH_LAUNCH_RRC
     DH_CUDA(cudaGetLastError());

@@ -134,3 +134,18 @@ def test_rrc_custom_taps_and_argument_errors():
     bank.close()
     with pytest.raises(dh.DhError):
         dh.RrcBank(2, custom=(30, 1.0, np.zeros(31, np.float32)))  # nZeros not a multiple of 4
+
+
+def test_rrc_more_channels_than_grid_y():
+    """banks beyond 65535 channels are launched in channel slices (grid.y limit); history carries per channel"""
+    import digiham_b200 as dh
+    C, n = 65535 + 9, 300
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-1, 1, (C, 2 * n)).astype(np.float32)
+    bank = dh.RrcBank(C, dh.RRC_WIDE)
+    xd = torch.from_numpy(x).cuda()
+    y = torch.cat([bank.process(xd[:, :n].contiguous()), bank.process(xd[:, n:].contiguous())], dim=1).cpu().numpy()
+    orc = oracle_lib.best()
+    for ch in (0, 1, 65534, 65535, 65536, C - 1):
+        assert np.array_equal(_bits(y[ch]), _bits(orc.rrc(x[ch]))), ch
+    bank.close()
