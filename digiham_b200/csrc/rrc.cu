@@ -35,10 +35,14 @@ constexpr int kRDefault = 17;         // outputs per thread; odd, see the kernel
 constexpr int kMaxTile = kThreads * 19;
 constexpr int kMaxZeros = 1024;
 constexpr int kMaxTapsParam = 164;    // taps that travel in the kernel parameter (constant bank 0)
+// The parameter copy is laid out in groups of R taps padded to a multiple of 4 floats, so that the rolled loop
+// fetches the taps of one group with 16-byte uniform loads (LDCU.128) instead of one LDCU per tap.
+constexpr int kTapSlots = 224;        // >= groups * pad4(R) for 164 taps at R = 13
 
-struct TapBlock {
-    float c[kMaxTapsParam];
+struct alignas(16) TapBlock {
+    float c[kTapSlots];
 };
+__host__ __device__ constexpr int pad4(int r) { return (r + 3) & ~3; }
 
 struct RrcParams {
     const float* in;
@@ -152,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
             const float* nxt = sw + i0 + kR;
 #pragma unroll
             for (int k = 0; k < kR; k++) {
-                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
+                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[it * pad4(kR) + k];
 #pragma unroll
                 for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
                 // slot k held s[base + i0 + k] (the oldest sample, last used by r = 0); it now receives the
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
 #pragma unroll
         for (int k = 0; k < kR - 1; k++) {
             if (k < rem) {
-                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[i0 + k];
+                const float c = taps_in_smem ? s_taps[i0 + k] : taps.c[full * pad4(kR) + k];
 #pragma unroll
                 for (int r = 0; r < kR; r++) acc[r] = __fadd_rn(acc[r], __fmul_rn(c, w[(r + k) % kR]));
                 if (i0 + k < nz) w[k] = nxt[k];
@@ -201,7 +205,9 @@ struct dh_rrc {
     int nz = 0;
     double gain = 1.0;
     int mul_recip = 0;
-    TapBlock taps{};
+    float flat_taps[kMaxTapsParam] = {0};   // taps 0..min(nz, kMaxTapsParam - 1) in order
+    TapBlock taps{};                        // grouped layout for `taps_r` outputs per thread
+    int taps_r = 0;
     float* d_taps = nullptr;   // global copy, used for long custom filters
     float* d_hist = nullptr;   // [2][channels][nz]
     int cur = 0;
@@ -232,7 +238,7 @@ int rrc_build(dh_rrc** out, int device, uint32_t channels, uint32_t nz, double g
     h->nz = (int) nz;
     h->gain = mul_recip ? 1.0 / gain : gain;
     h->mul_recip = mul_recip;
-    for (uint32_t i = 0; i <= nz && i < (uint32_t) kMaxTapsParam; i++) h->taps.c[i] = coeffs[i];
+    for (uint32_t i = 0; i <= nz && i < (uint32_t) kMaxTapsParam; i++) h->flat_taps[i] = coeffs[i];
     size_t hist_bytes = 2 * (size_t) channels * nz * sizeof(float);
     cudaError_t e = cudaMalloc(&h->d_hist, hist_bytes);
     if (e == cudaSuccess) e = cudaMemset(h->d_hist, 0, hist_bytes);
@@ -315,6 +321,11 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
     p.pad_ = 0;
 
     cudaStream_t st = (cudaStream_t) stream;
+    if (h->taps_r != r) {   // (re)build the grouped parameter layout for this R
+        std::memset(&h->taps, 0, sizeof(h->taps));
+        for (int i = 0; i <= h->nz && i < kMaxTapsParam; i++) h->taps.c[(i / r) * pad4(r) + i % r] = h->flat_taps[i];
+        h->taps_r = r;
+    }
     size_t smem = (size_t) (h->nz + tile) * sizeof(float);
     const int which = h->nz == 80 && h->mul_recip ? 0 : (h->nz == 160 && h->mul_recip ? 1 : 2);
     if (which == 2 && h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
