@@ -15,6 +15,7 @@
 //   * the LICH of the last valid frame is kept when a new LICH fails its parity (nxdn_phase.cpp:64-69).
 #include "decoder_ops.hpp"
 #include "viterbi.cuh"
+#include "crc_par.cuh"
 
 #include <cstring>
 
@@ -74,7 +75,15 @@ __host__ __device__ constexpr PnTable make_pn() {
 }
 __constant__ PnTable c_nx_pn = make_pn();
 
+// Sacch::check_crc / Facch1::check_crc as warp-parallel table look-ups (crc_par.cuh)
+__constant__ CrcTable<26> c_crc6 = make_crc_table<1, 26>();
+__constant__ CrcTable<80> c_crc12 = make_crc_table<2, 80>();
+struct NxdnCrcTables {
+    uint16_t t6[26], t12[80];
+};
+
 struct NCtx {
+    const NxdnCrcTables* crc;
     NxdnState st;
     DecWriter w;
     uint8_t* body;      // 182 descrambled dibits of the frame (shared memory)
@@ -115,12 +124,7 @@ __device__ bool parse_sacch(NCtx& c, const uint8_t* in, uint32_t& word) {
     uint32_t words[2];
     viterbi<36, true>(dib, c.lane, words);
     __syncwarp();
-    uint32_t crc = 0x3F;
-    for (int i = 0; i < 26; i++) {
-        const uint32_t cb = ((crc >> 5) & 1u) ^ ((words[0] >> (31 - i)) & 1u);
-        if (cb) crc ^= 0x13;
-        crc = ((crc << 1) & 0x3Eu) | cb;
-    }
+    const uint32_t crc = crc_parallel<26>(words, c.crc->t6, c_crc6.c, c.lane);
     if ((words[0] & 0x3Fu) != crc) return false;
     word = words[0];
     return true;
@@ -148,12 +152,7 @@ __device__ int parse_facch1(NCtx& c, const uint8_t* in) {
     uint32_t words[3];
     viterbi<96, true>(dib, c.lane, words);
     __syncwarp();
-    uint32_t crc = 0xFFF;
-    for (int i = 0; i < 80; i++) {
-        const uint32_t cb = ((crc >> 11) & 1u) ^ ((words[i >> 5] >> (31 - (i & 31))) & 1u);
-        if (cb) crc ^= 0x407;
-        crc = ((crc << 1) & 0xFFEu) | cb;
-    }
+    const uint32_t crc = crc_parallel<80>(words, c.crc->t12, c_crc12.c, c.lane);
     const uint32_t to_check = (words[2] >> 4) & 0xFFFu;   // bits 80..91
     if (to_check != crc) return -1;
     return (int) ((words[0] >> 24) & 0x3Fu);
@@ -263,6 +262,12 @@ __global__ void __launch_bounds__(kNWarps * 32) nxdn_kernel(const __grid_constan
     __shared__ __align__(16) uint8_t s_fr[kNWarps][kNxFrame];
     __shared__ __align__(16) uint8_t s_body[kNWarps][kNxFrame];
     __shared__ __align__(16) uint8_t s_scratch[kNWarps][96];
+    __shared__ NxdnCrcTables s_crc;
+    for (int i = threadIdx.x; i < 80; i += kNWarps * 32) {
+        if (i < 26) s_crc.t6[i] = c_crc6.t[i];
+        s_crc.t12[i] = c_crc12.t[i];
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ch = blockIdx.x * kNWarps + warp;
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(kNWarps * 32) nxdn_kernel(const __grid_constan
     NCtx c;
     c.st = states[ch];
     c.lane = lane;
+    c.crc = &s_crc;
     c.body = s_body[warp];
     c.scratch = s_scratch[warp];
     c.w.out = io.out + (size_t) ch * io.out_cap;

@@ -14,6 +14,7 @@
 // Metrics are kept modulo 256 like the reference's uint8_t (trellis.c:28,68).
 #include "decoder_ops.hpp"
 #include "viterbi.cuh"
+#include "crc_par.cuh"
 
 #define DH_TABLES_NO_HOST_ARRAYS
 #include "tables.inc"
@@ -94,19 +95,13 @@ __constant__ uint8_t c_v2_inverse[49] = {0,  18, 36, 1,  19, 37, 2,  20, 38, 3, 
                                         41, 6,  24, 42, 7,  25, 43, 8,  26, 44, 9,  27, 45, 10, 28, 46, 11,
                                         29, 47, 12, 30, 48, 13, 31, 14, 32, 15, 33, 16, 34, 17, 35};
 
-// crc16_checksum (crc16.c:3-19): CCITT polynomial 0x1021, MSB first, init 0, inverted at the end
-__device__ __forceinline__ uint32_t crc16_bytes(const uint8_t* d, int count) {
-    uint32_t crc = 0;
-    for (int k = 0; k < count; k++) {
-        for (int i = 0; i < 8; i++) {
-            const uint32_t in = (d[k] >> (7 - i)) & 1u;
-            const uint32_t nx = in ^ ((crc >> 15) & 1u);
-            crc = (crc << 1) & 0xFFFFu;
-            crc ^= (nx << 12) | (nx << 5) | nx;
-        }
-    }
-    return crc ^ 0xFFFFu;
-}
+// crc16_checksum (crc16.c:3-19) over 32 / 80 / 160 message bits, evaluated warp-parallel (crc_par.cuh)
+__constant__ CrcTable<32> c_crc32 = make_crc_table<0, 32>();
+__constant__ CrcTable<80> c_crc80 = make_crc_table<0, 80>();
+__constant__ CrcTable<160> c_crc160 = make_crc_table<0, 160>();
+struct YsfCrcTables {   // copy in shared memory: lanes index the tables with different offsets
+    uint16_t t32[32], t80[80], t160[160];
+};
 
 __device__ __forceinline__ bool fec_golay24(uint32_t& w) {
     uint32_t s = 0;
@@ -121,6 +116,7 @@ __device__ __forceinline__ bool fec_golay24(uint32_t& w) {
 struct YCtx {
     YsfState st;
     DecWriter w;
+    const YsfCrcTables* crc;   // shared-memory copy of the CRC tables
     const uint8_t* fr;   // 480 staged dibits of the frame (shared memory)
     uint8_t* scratch;    // 192 bytes of per-warp scratch (shared memory)
     int lane;
@@ -169,8 +165,8 @@ __device__ bool parse_fich(YCtx& c, uint32_t& fich_out) {
     if (!ok) return false;
     const uint32_t fich = ((g[0] & 0xFFF000u) << 8) | ((g[1] & 0xFFF000u) >> 4) | ((g[2] & 0xFF0000u) >> 16);
     const uint32_t checksum = (g[2] & 0x00F000u) | ((g[3] & 0xFFF000u) >> 12);
-    const uint8_t be[4] = {(uint8_t) (fich >> 24), (uint8_t) (fich >> 16), (uint8_t) (fich >> 8), (uint8_t) fich};
-    if (crc16_bytes(be, 4) != checksum) return false;
+    // crc16 over the four FICH bytes, big endian (fich.cpp:44-49)
+    if (crc_parallel<32>(&fich, c.crc->t32, c_crc32.c, c.lane) != checksum) return false;
     fich_out = fich;
     return true;
 }
@@ -224,7 +220,7 @@ __device__ void v2_data_channel(YCtx& c, const uint8_t* payload, int frameNumber
 #pragma unroll
     for (int k = 0; k < 12; k++) raw[k] = word_byte(words, k);
     const uint32_t checksum = ((uint32_t) raw[10] << 8) | raw[11];
-    if (crc16_bytes(raw, 10) != checksum) return;
+    if (crc_parallel<80>(words, c.crc->t80, c_crc80.c, c.lane) != checksum) return;
     // decode_whitening(..., 100): the first 100 bits are de-whitened, i.e. all of the 10 bytes used below
     uint8_t dch[10];
 #pragma unroll
@@ -262,7 +258,7 @@ __device__ bool header_data_channel(YCtx& c, const uint8_t* in, uint8_t* dch20) 
 #pragma unroll
     for (int k = 0; k < 22; k++) raw[k] = word_byte(words, k);
     const uint32_t checksum = ((uint32_t) raw[20] << 8) | raw[21];
-    if (crc16_bytes(raw, 20) != checksum) return false;
+    if (crc_parallel<160>(words, c.crc->t160, c_crc160.c, c.lane) != checksum) return false;
 #pragma unroll
     for (int k = 0; k < 20; k++) dch20[k] = dewhitened_byte(words, k);
     return true;
@@ -371,6 +367,13 @@ constexpr int kYWarps = 4;
 __global__ void __launch_bounds__(kYWarps * 32) ysf_kernel(const __grid_constant__ DecIo io, YsfState* states) {
     __shared__ __align__(16) uint8_t s_fr[kYWarps][kYsfFrame];
     __shared__ __align__(16) uint8_t s_scratch[kYWarps][192];
+    __shared__ YsfCrcTables s_crc;
+    for (int i = threadIdx.x; i < 160; i += kYWarps * 32) {
+        if (i < 32) s_crc.t32[i] = c_crc32.t[i];
+        if (i < 80) s_crc.t80[i] = c_crc80.t[i];
+        s_crc.t160[i] = c_crc160.t[i];
+    }
+    __syncthreads();
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ch = blockIdx.x * kYWarps + warp;
@@ -379,6 +382,7 @@ __global__ void __launch_bounds__(kYWarps * 32) ysf_kernel(const __grid_constant
     YCtx c;
     c.st = states[ch];
     c.lane = lane;
+    c.crc = &s_crc;
     c.fr = s_fr[warp];
     c.scratch = s_scratch[warp];
     c.w.out = io.out + (size_t) ch * io.out_cap;
