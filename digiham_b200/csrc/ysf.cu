@@ -118,7 +118,7 @@ struct YCtx {
     DecWriter w;
     const YsfCrcTables* crc;   // shared-memory copy of the CRC tables
     const uint8_t* fr;   // 480 staged dibits of the frame (shared memory)
-    uint8_t* scratch;    // 192 bytes of per-warp scratch (shared memory)
+    uint8_t* scratch;    // 384 bytes of per-warp scratch (shared memory): two dibit arrays for the paired Viterbi
     int lane;
 };
 
@@ -145,15 +145,8 @@ __device__ __forceinline__ uint8_t word_byte(const uint32_t* words, int k) {
     return (uint8_t) (words[k >> 2] >> (24 - 8 * (k & 3)));
 }
 
-// Fich::parse (fich.cpp:12-52)
-__device__ bool parse_fich(YCtx& c, uint32_t& fich_out) {
-    const uint8_t* data = c.fr + kYsfSync;
-    uint8_t* dib = c.scratch;
-    for (int i = c.lane; i < 100; i += 32) dib[i] = data[(i * 20) % 100 + (i * 20) / 100] & 3u;
-    __syncwarp();
-    uint32_t words[4];
-    viterbi<100, false>(dib, c.lane, words);
-    __syncwarp();
+// Fich::parse (fich.cpp:12-52) behind the Viterbi decoder: `words` = the 100 decoded bits
+__device__ bool parse_fich(YCtx& c, const uint32_t* words, uint32_t& fich_out) {
     uint32_t g[4];
     bool ok = true;
 #pragma unroll
@@ -208,14 +201,8 @@ __device__ __forceinline__ uint8_t dewhitened_byte(const uint32_t* words, int k)
     return (uint8_t) ((words[k >> 2] ^ c_pn.w[k >> 2]) >> (24 - 8 * (k & 3)));
 }
 
-// FramePhase::decodeV2DataChannel (ysf_phase.cpp:258-306)
-__device__ void v2_data_channel(YCtx& c, const uint8_t* payload, int frameNumber) {
-    uint8_t* dib = c.scratch;
-    for (int i = c.lane; i < 100; i += 32) dib[i] = payload[(i % 5) * 72 + (i * 2) / 10] & 3u;
-    __syncwarp();
-    uint32_t words[4];
-    viterbi<100, false>(dib, c.lane, words);
-    __syncwarp();
+// FramePhase::decodeV2DataChannel (ysf_phase.cpp:258-306) behind the Viterbi decoder: `words` = its 100 decoded bits
+__device__ void v2_data_channel(YCtx& c, const uint32_t* words, int frameNumber) {
     uint8_t raw[12];
 #pragma unroll
     for (int k = 0; k < 12; k++) raw[k] = word_byte(words, k);
@@ -243,17 +230,8 @@ __device__ void v2_data_channel(YCtx& c, const uint8_t* payload, int frameNumber
     }
 }
 
-// FramePhase::decodeHeaderDataChannel (ysf_phase.cpp:317-349); in = payload (+36 for the second channel)
-__device__ bool header_data_channel(YCtx& c, const uint8_t* in, uint8_t* dch20) {
-    uint8_t* dib = c.scratch;
-    for (int i = c.lane; i < 180; i += 32) {
-        const int streampos = (i % 9) * 20 + i / 9;
-        dib[i] = in[(streampos / 36) * 72 + streampos % 36] & 3u;
-    }
-    __syncwarp();
-    uint32_t words[6];
-    viterbi<180, false>(dib, c.lane, words);
-    __syncwarp();
+// FramePhase::decodeHeaderDataChannel (ysf_phase.cpp:317-349) behind the Viterbi decoder: `words` = 180 decoded bits
+__device__ bool header_data_channel(YCtx& c, const uint32_t* words, uint8_t* dch20) {
     uint8_t raw[22];
 #pragma unroll
     for (int k = 0; k < 22; k++) raw[k] = word_byte(words, k);
@@ -287,13 +265,27 @@ __device__ bool ysf_frame(YCtx& c) {
         return false;
     }
 
+    // K5: the FICH and — speculatively, the second half-warp would otherwise repeat the first — the data channel
+    // of a V/D2 frame are decoded side by side (fich.cpp:12-22, ysf_phase.cpp:258-272)
+    const uint8_t* payload = c.fr + kYsfSync + kYsfFich;
+    uint32_t fich_words[4], dch_words[4], vm_a, vm_b;
+    {
+        const uint8_t* data = c.fr + kYsfSync;
+        uint8_t* dib = c.scratch;
+        for (int i = lane; i < 100; i += 32) {
+            dib[i] = data[(i * 20) % 100 + (i * 20) / 100] & 3u;
+            dib[192 + i] = payload[(i % 5) * 72 + (i * 2) / 10] & 3u;
+        }
+        __syncwarp();
+        viterbi_pair<100, false>(dib, dib + 192, lane, fich_words, dch_words, vm_a, vm_b);
+        __syncwarp();
+    }
     uint32_t fich = 0;
-    const bool fich_ok = parse_fich(c, fich);
+    const bool fich_ok = parse_fich(c, fich_words, fich);
     if (fich_ok) {
         s.has_fich = 1;
         s.fich = fich;
     }
-    const uint8_t* payload = c.fr + kYsfSync + kYsfFich;
     if (s.has_fich) {
         const int frameType = (s.fich >> 30) & 3;
         const int dataType = (s.fich >> 8) & 3;
@@ -319,7 +311,7 @@ __device__ bool ysf_frame(YCtx& c) {
                     }
                     c.w.out_len += 40;
                 }
-                if (fich_ok) v2_data_channel(c, payload, (int) ((fich >> 19) & 7));
+                if (fich_ok) v2_data_channel(c, dch_words, (int) ((fich >> 19) & 7));
             } else if (dataType == 3) {   // voice full rate
                 meta_mode(c, 3);
                 const int start = s.expectSubFrame ? 3 : 0;
@@ -344,12 +336,26 @@ __device__ bool ysf_frame(YCtx& c) {
         } else if (frameType == 0) {      // header
             meta_reset(c);
             c.w.event(lane, kYsfEvHold, 0);
+            // both 180-step data channels of the header in one paired decode (ysf_phase.cpp:139-161, 317-331)
+            uint32_t h0[6], h1[6];
+            {
+                uint8_t* dib = c.scratch;
+                for (int i = lane; i < 180; i += 32) {
+                    const int streampos = (i % 9) * 20 + i / 9;
+                    const int at = (streampos / 36) * 72 + streampos % 36;
+                    dib[i] = payload[at] & 3u;
+                    dib[192 + i] = payload[36 + at] & 3u;
+                }
+                __syncwarp();
+                viterbi_pair<180, false>(dib, dib + 192, lane, h0, h1, vm_a, vm_b);
+                __syncwarp();
+            }
             uint8_t dch[20];
-            if (header_data_channel(c, payload, dch)) {
+            if (header_data_channel(c, h0, dch)) {
                 meta_field(c, 0, dch);
                 meta_field(c, 1, dch + 10);
             }
-            if (header_data_channel(c, payload + 36, dch)) {
+            if (header_data_channel(c, h1, dch)) {
                 meta_field(c, 2, dch);
                 meta_field(c, 3, dch + 10);
             }
@@ -366,7 +372,7 @@ constexpr int kYWarps = 4;
 
 __global__ void __launch_bounds__(kYWarps * 32) ysf_kernel(const __grid_constant__ DecIo io, YsfState* states) {
     __shared__ __align__(16) uint8_t s_fr[kYWarps][kYsfFrame];
-    __shared__ __align__(16) uint8_t s_scratch[kYWarps][192];
+    __shared__ __align__(16) uint8_t s_scratch[kYWarps][384];
     __shared__ YsfCrcTables s_crc;
     for (int i = threadIdx.x; i < 160; i += kYWarps * 32) {
         if (i < 32) s_crc.t32[i] = c_crc32.t[i];
