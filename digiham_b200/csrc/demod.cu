@@ -43,6 +43,8 @@ struct ChannelState {
 struct DemodParams {
     const float* work;           // [channels][pitch] rows read by this call; chunk sample 0 at column carry_cap
     float* work_next;            // rows the next call reads: receives the carried tail
+    const float* ext;            // non-null: the chunk lives in the CALLER's rows (16-byte aligned), only the carried
+    unsigned long long ext_pitch;  //         tail comes from `work`; null: the chunk follows the tail inside `work`
     unsigned long long pitch;
     uint8_t* sym;                // [channels][sym_pitch]
     unsigned long long sym_pitch;
@@ -213,13 +215,41 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
     const float fsps = (float) sps;
     const float fwin = (float) (hi - lo);
 
+    // Logical stream = carried tail (in `work`) followed by the chunk: either right behind it in the same row
+    // (a producer kernel wrote it there) or in the caller's own rows (`ext`), which are then read in place.
+    const float* ext_row = p.ext ? p.ext + (size_t) ch * p.ext_pitch : nullptr;
+    auto at = [&](int x) -> const float* {
+        return (ext_row != nullptr && x >= carry_len) ? ext_row + (x - carry_len) : row + col0 + x;
+    };
+    // offset of sample P inside its 16-byte unit (0 for a block that starts in the tail of an `ext` call: that
+    // block is copied element by element because it straddles two buffers)
+    auto align_of = [&](int P) -> int {
+        if (ext_row == nullptr) return (col0 + P) & 3;
+        return P >= carry_len ? (P - carry_len) & 3 : 0;
+    };
     // asynchronous staging of [P, P + m*sps + 2) with aligned 16-byte copies; sample P + x lands at S[a0 + x]
     auto stage = [&](int P, int m) {
-        const int a0 = (col0 + P) & 3;
-        const float4* src = reinterpret_cast<const float4*>(row + col0 + P - a0);
-        float4* dst = reinterpret_cast<float4*>(S);
-        const int nvec = (a0 + m * sps + 2 + 3) >> 2;
-        for (int v = gl; v < nvec; v += G) cp_async16(dst + v, src + v);
+        const int a0 = align_of(P);
+        const int len = m * sps + 2;
+        if (ext_row == nullptr) {
+            const float4* src = reinterpret_cast<const float4*>(row + col0 + P - a0);
+            float4* dst = reinterpret_cast<float4*>(S);
+            const int nvec = (a0 + len + 3) >> 2;
+            for (int v = gl; v < nvec; v += G) cp_async16(dst + v, src + v);
+        } else if (P >= carry_len) {
+            // whole vectors as long as they end inside the caller's row, single samples behind them (never read
+            // past sample T - 1: the buffer is not ours)
+            const float* base = ext_row + (P - carry_len) - a0;
+            const int avail = T - P + a0;                       // floats from `base` to the end of the chunk
+            const int want = a0 + len;
+            const int nvec = min(want, avail) >> 2;
+            const float4* src = reinterpret_cast<const float4*>(base);
+            float4* dst = reinterpret_cast<float4*>(S);
+            for (int v = gl; v < nvec; v += G) cp_async16(dst + v, src + v);
+            for (int x = 4 * nvec + gl; x < min(want, avail); x += G) cp_async4(S + x, base + x);
+        } else {
+            for (int x = gl; x < len && P + x < T; x += G) cp_async4(S + x, at(P + x));
+        }
         cp_async_commit();
     };
 
@@ -232,7 +262,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
         __syncwarp(gmask);
     }
     while (m > j_done) {
-        const int a0 = (col0 + P) & 3;
+        const int a0 = align_of(P);
 
         // window sums of the symbols this lane owns (gfsk_demodulator.cpp:28-35, 82-83, 88)
         float volr[CH], avgr[CH];
@@ -392,10 +422,9 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
     {
         // through the (now idle) sample buffer, so that all loads are in flight at once instead of one
         // load->store round trip per element
-        const float* src = row + col0 + P;
         float* dst = p.work_next + (size_t) ch * p.pitch + p.carry_cap - keep;
         __syncwarp(gmask);   // every lane of the group is done reading the staged block (window sums of a partial block)
-        for (int idx = gl; idx < keep; idx += G) cp_async4(S + idx, src + idx);
+        for (int idx = gl; idx < keep; idx += G) cp_async4(S + idx, at(P + idx));
         cp_async_commit();
         cp_async_wait_all();
         __syncwarp(gmask);
@@ -528,17 +557,24 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
                dh_demod_max_symbols(h, n));
     const bool zero_copy =
         h->d_work[0] && d_in == h->d_work[h->cur] + h->carry_cap && in_pitch == h->pitch && n <= h->max_n;
+    // any other 16-byte aligned device buffer is read in place (only the carried tails live in the work rows);
+    // unaligned rows are copied behind the tails first
+    const bool in_place = !zero_copy && reinterpret_cast<uintptr_t>(d_in) % 16 == 0 && in_pitch % 4 == 0;
     if (!zero_copy) {
         DH_REQUIRE(in_pitch >= n, DH_E_INVALID, "dh_demod_process: in_pitch < n");
-        int rc = demod_reserve(h, n);
+        int rc = demod_reserve(h, in_place ? 0 : n);
         if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->d_work[h->cur] + h->carry_cap, h->pitch * sizeof(float), d_in, in_pitch * sizeof(float),
-                                  n * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, st));
+        if (!in_place) {
+            DH_CUDA(cudaMemcpy2DAsync(h->d_work[h->cur] + h->carry_cap, h->pitch * sizeof(float), d_in,
+                                      in_pitch * sizeof(float), n * sizeof(float), h->channels, cudaMemcpyDeviceToDevice, st));
+        }
     }
 
     DemodParams p;
     p.work = h->d_work[h->cur];
     p.work_next = h->d_work[h->cur ^ 1];
+    p.ext = in_place ? d_in : nullptr;
+    p.ext_pitch = in_pitch;
     p.pitch = h->pitch;
     p.sym = d_sym;
     p.sym_pitch = sym_pitch;

@@ -86,7 +86,8 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
         else rc = dh_demod_create(&h->demod, device, channels, 1, nxdn ? 20 : 10, 0);
     }
     if (rc == DH_OK) rc = dh_decoder_create(&h->decoder, device, channels, proto);
-    if (rc == DH_OK) rc = dh_demod_reserve(h->demod, max_chunk, &h->d_filt, &h->filt_pitch);
+    // pipes without an RRC stage hand the caller's block to the demodulator, which reads it in place
+    if (rc == DH_OK && h->rrc) rc = dh_demod_reserve(h->demod, max_chunk, &h->d_filt, &h->filt_pitch);
     if (rc == DH_OK) {
         h->max_syms = dh_demod_max_symbols(h->demod, max_chunk);
         rc = dh_decoder_reserve(h->decoder, h->max_syms, &h->d_sym, &h->sym_pitch);
