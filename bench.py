@@ -277,6 +277,19 @@ def main():
             pipe.decoder.clear()
 
         e2e_steps(min(args.warmup, 3))
+        # the link itself: the same pinned block copied host -> device with nothing else going on
+        link = torch.empty((C, pitch), dtype=torch.float32, device=dev)
+        for _ in range(2):
+            link.copy_(xh, non_blocking=True)
+        torch.cuda.synchronize()
+        l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0.record(stream)
+        for _ in range(5):
+            link.copy_(xh, non_blocking=True)
+        l1.record(stream)
+        torch.cuda.synchronize()
+        link_ms = l0.elapsed_time(l1) / 5
+        del link
         _, d2h0 = pipe.decoder.stats()
         k_e2e = args.steps
         barrier()
@@ -294,6 +307,9 @@ def main():
         e2e = {"value": world * C * L * k_e2e / dt / 1e6, "unit": "Msamples/s",
                "h2d_bytes_per_step": C * pitch * 4, "d2h_bytes_per_step": (d2h1 - d2h0) // k_e2e,
                "steps": k_e2e, "ms_per_step": dt / k_e2e * 1e3,
+               "h2d_copy_only": {"ms_per_step_block": link_ms, "GBps": C * pitch * 4 / link_ms / 1e6,
+                                 "Msamples_per_s": C * L / link_ms / 1e3,
+                                 "note": "pinned host -> device copy of one step's block alone: the PCIe ceiling of e2e"},
                "path": "dh_pipe_submit_host (pinned H2D + 3 kernels) / dh_pipe_collect_step (D2H + metadata replay) per "
                        "step, two steps in flight"}
     clocks = sampler.stop() if rank == 0 else None
