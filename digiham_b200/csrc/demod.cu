@@ -367,6 +367,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
 
         // calibrateAudio + slicing (gfsk_demodulator.cpp:88-104, 109-122)
         float rmn = emn, rmx = emx;
+        uint8_t* const sym_out = sym_row + (emitted - j_done + j_first);   // this lane's symbol q goes to sym_out[q]
 #pragma unroll
         for (int q = 0; q < CH; q++) {
             const int j = j_first + q;
@@ -389,7 +390,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
                     } else {
                         s = a > center ? (p.invert ? 0 : 1) : (p.invert ? 1 : 0);
                     }
-                    sym_row[emitted + (j - j_done)] = s;
+                    sym_out[q] = s;
                 }
             }
         }
