@@ -87,6 +87,18 @@ __device__ __forceinline__ void carry_symbols(uint8_t* row, int carry_cap, int c
 
 __device__ __forceinline__ uint32_t parity32(uint32_t v) { return __popc(v) & 1u; }
 
+// Stage `count` symbols starting at src into a 4-byte aligned shared buffer with aligned 32-bit loads; returns the
+// address of the first symbol inside the buffer (buffer size >= count + 4; symbol rows are 16-byte aligned, so no
+// word leaves the row).  The caller synchronises the warp afterwards.
+__device__ __forceinline__ const uint8_t* stage_symbols(uint8_t* buf, const uint8_t* src, int count, int lane) {
+    const int mis = (int) (reinterpret_cast<uintptr_t>(src) & 3u);
+    const uint32_t* src_w = reinterpret_cast<const uint32_t*>(src - mis);
+    uint32_t* dst_w = reinterpret_cast<uint32_t*>(buf);
+    const int nwords = (count + mis + 3) >> 2;
+    for (int i = lane; i < nwords; i += 32) dst_w[i] = src_w[i];
+    return buf + mis;
+}
+
 #endif  // __CUDACC__
 
 // Host side of a bank: per-channel accumulated results between dh_decoder_collect calls.

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kDWarps * 32) dstar_kernel(const __grid_consta
         } else if (s.phase == 1) {
             // HeaderPhase (dstar_phase.cpp:37-59)
             if (T - pos <= kDsHeader) break;
-            for (int i = lane; i < kDsHeader; i += 32) c.buf[i] = stream[pos + i];
+            for (int i = lane; i < kDsHeader; i += 32) c.buf[i] = stream[pos + i];   // rare: once per transmission
             __syncwarp();
             if (!parse_header(c)) {
                 pos += 1;

@@ -259,7 +259,7 @@ __device__ int nxdn_frame(NCtx& c, const uint8_t* fr, bool& to_sync) {
 constexpr int kNWarps = 4;
 
 __global__ void __launch_bounds__(kNWarps * 32) nxdn_kernel(const __grid_constant__ DecIo io, NxdnState* states) {
-    __shared__ __align__(16) uint8_t s_fr[kNWarps][kNxFrame];
+    __shared__ __align__(16) uint8_t s_fr[kNWarps][kNxFrame + 8];
     __shared__ __align__(16) uint8_t s_body[kNWarps][kNxFrame];
     __shared__ __align__(16) uint8_t s_scratch[kNWarps][96];
     __shared__ NxdnCrcTables s_crc;
@@ -319,10 +319,10 @@ __global__ void __launch_bounds__(kNWarps * 32) nxdn_kernel(const __grid_constan
             }
         } else {
             if (T - pos <= kNxFrame) break;
-            for (int i = lane; i < kNxFrame; i += 32) s_fr[warp][i] = stream[pos + i];
+            const uint8_t* fr = stage_symbols(s_fr[warp], stream + pos, kNxFrame, lane);
             __syncwarp();
             bool to_sync;
-            pos += nxdn_frame(c, s_fr[warp], to_sync);
+            pos += nxdn_frame(c, fr, to_sync);
             if (to_sync) c.st.phase = 0;
             __syncwarp();
         }

@@ -371,7 +371,7 @@ __device__ bool ysf_frame(YCtx& c) {
 constexpr int kYWarps = 4;
 
 __global__ void __launch_bounds__(kYWarps * 32) ysf_kernel(const __grid_constant__ DecIo io, YsfState* states) {
-    __shared__ __align__(16) uint8_t s_fr[kYWarps][kYsfFrame];
+    __shared__ __align__(16) uint8_t s_fr[kYWarps][kYsfFrame + 8];
     __shared__ __align__(16) uint8_t s_scratch[kYWarps][384];
     __shared__ YsfCrcTables s_crc;
     for (int i = threadIdx.x; i < 160; i += kYWarps * 32) {
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(kYWarps * 32) ysf_kernel(const __grid_constant
             }
         } else {
             if (T - pos <= kYsfFrame) break;
-            for (int i = lane; i < kYsfFrame; i += 32) s_fr[warp][i] = stream[pos + i];
+            c.fr = stage_symbols(s_fr[warp], stream + pos, kYsfFrame, lane);
             __syncwarp();
             if (ysf_frame(c)) pos += kYsfFrame;
             else c.st.phase = 0;
