@@ -63,10 +63,12 @@ struct RrcParams {
 // surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..19 to
 // minimise tiles * (work per tile): e.g. n = 48000 -> R = 15, 25 full tiles instead of 22 + a ragged one at R = 17.
 inline int pick_r(size_t n, int nz) {
-    if (const char* env = getenv("DH_RRC_R")) {   // experiment switch
-        const int r = atoi(env);
-        if (r == 13 || r == 15 || r == 17 || r == 19) return r;
-    }
+    static const int forced = [] {   // tuning switch, read once
+        const char* env = getenv("DH_RRC_R");
+        const int r = env ? atoi(env) : 0;
+        return (r == 13 || r == 15 || r == 17 || r == 19) ? r : 0;
+    }();
+    if (forced) return forced;
     int best = kRDefault;
     double best_cost = 1e300;
     for (int r = 19; r >= 13; r -= 2) {
