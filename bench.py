@@ -32,6 +32,49 @@ METRIC = "Msamples/s RRC->GFSK->DMR pipe"
 ALGO_BYTES_PER_SAMPLE_K1 = 8.0       # K1 stand-alone: 4 B in + 4 B out
 ALGO_BYTES_PER_SAMPLE_PIPE = 4.119   # fused-pipe figure, reported for context
 
+# The bench line is the DMR pipe (BASELINE configs[1]).  `--workload` runs the other pipes through the same
+# harness (BASELINE configs[2] / [4] and the SURVEY 8f decoders): name, default channels per GPU, samples per
+# symbol, dominant stage (0 = K1 RRC, 1 = K2 demodulator) and its algorithmic bytes per sample.
+WORKLOADS = {
+    "dmr": dict(channels=4096, sps=10, dominant=0, algo=8.0, pipe_bytes=4.119,
+                desc="WideRrcFilter -> GfskDemodulator(10) -> Dmr::Decoder (BASELINE configs[1])"),
+    "ysf": dict(channels=8192, sps=10, dominant=0, algo=8.0, pipe_bytes=4.12,
+                desc="WideRrcFilter -> GfskDemodulator(10) -> Ysf::Decoder (BASELINE configs[2])"),
+    "nxdn": dict(channels=4096, sps=20, dominant=0, algo=8.0, pipe_bytes=4.06,
+                 desc="NarrowRrcFilter -> GfskDemodulator(20) -> Nxdn::Decoder (SURVEY 8f rank 1)"),
+    "dstar": dict(channels=8192, sps=10, dominant=1, algo=4.1, pipe_bytes=4.11,
+                  desc="FskDemodulator(10) -> DStar::Decoder (SURVEY 8f rank 3)"),
+    "pocsag": dict(channels=32768, sps=40, dominant=1, algo=4.025, pipe_bytes=4.03,
+                   desc="FskDemodulator(40, invert) -> Pocsag::Decoder (BASELINE configs[4])"),
+}
+
+
+def workload_signal(name, channels, n, seed, device):
+    """Seeded synthetic input [channels, pitch] float32 of one workload (device or cpu)."""
+    import numpy as np
+    from digiham_b200 import synth
+    if name == "dmr":
+        return synth.dmr_channel_bank(channels, n, seed=seed, device=device)[0]
+    w = WORKLOADS[name]
+    gen = {"ysf": lambda k: synth.ysf_symbols(12, seed=seed * 131 + k, mode="mix", lead_in=0),
+           "nxdn": lambda k: synth.nxdn_symbols(16, seed=seed * 131 + k, lead_in=0),
+           "dstar": lambda k: np.concatenate([np.tile(np.array([1, 0], dtype=np.uint8), 100),
+                                              synth.dstar_symbols(60, seed=seed * 131 + k, lead_in=0)]),
+           "pocsag": lambda k: synth.pocsag_bits([(1000 + k, 3, "B200 BENCH %d" % k), (77 + k, 3, "73")],
+                                                 seed=seed * 131 + k, lead_in=0, preamble=200)}[name]
+    levels = {"ysf": synth.LEVELS4, "nxdn": synth.LEVELS4, "dstar": synth.LEVELS2, "pocsag": synth.LEVELS2[::-1].copy()}[name]
+    nsym = n // w["sps"] + 8
+    pool = np.stack([np.resize(gen(k), nsym) for k in range(24)])
+    rng = np.random.default_rng(seed)
+    sym = np.empty((channels, nsym), dtype=np.uint8)
+    shifts = rng.integers(0, nsym, size=channels)
+    for c in range(channels):
+        sym[c] = np.roll(pool[c % 24], int(shifts[c]))
+    return synth.modulate_batch(sym, n, sps=w["sps"], levels=levels, amplitude=rng.choice([0.25, 0.5, 0.8], size=channels),
+                                ppm=rng.choice([0.0, 20.0, -20.0, 50.0, -50.0], size=channels),
+                                phase=rng.integers(0, 4 * w["sps"], size=channels).astype(np.float64),
+                                snr_db=rng.choice([np.inf, 20.0, 12.0, 8.0], size=channels), seed=seed + 1, device=device)
+
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -90,6 +133,14 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def proto_ids(name):
+    import oracle_lib
+    import digiham_b200 as dh
+    return {"dmr": (dh.PROTO_DMR, oracle_lib.PROTO_DMR), "ysf": (dh.PROTO_YSF, oracle_lib.PROTO_YSF),
+            "nxdn": (dh.PROTO_NXDN, oracle_lib.PROTO_NXDN), "dstar": (dh.PROTO_DSTAR, oracle_lib.PROTO_DSTAR),
+            "pocsag": (dh.PROTO_POCSAG, oracle_lib.PROTO_POCSAG)}[name]
+
+
 def reference_arm(args, x_host_rows, cores):
     """Times the reference CPU modules (or the port when the compiled reference is absent) on host cores.
     x_host_rows: float32 numpy [channels, n].  Returns (Msamples/s, kind, sample description, seconds/step)."""
@@ -99,7 +150,7 @@ def reference_arm(args, x_host_rows, cores):
     times = []
     for it in range(args.warmup_ref + args.steps_ref):
         t0 = time.perf_counter()
-        orc.pipe_batch(oracle_lib.PROTO_DMR, x_host_rows, threads=cores, chunk=4096)
+        orc.pipe_batch(args.orc_proto, x_host_rows, threads=cores, chunk=4096)
         dt = time.perf_counter() - t0
         if it >= args.warmup_ref:
             times.append(dt)
@@ -135,11 +186,10 @@ def bind_to_gpu_numa_node(local_rank):
         return "unavailable (%s)" % type(ex).__name__
 
 
-def build_host_sample(channels, n, seed):
+def build_host_sample(workload, channels, n, seed):
     """CPU-side generation of a bounded sample of the workload (used by --impl reference on a box whose GPU arm
     is not running): same generator, same seed, first `channels` channels."""
-    from digiham_b200 import synth
-    x, _ = synth.dmr_channel_bank(channels, n, seed=seed, device="cpu")
+    x = workload_signal(workload, channels, n, seed, "cpu")
     return x[:, :n].contiguous().numpy()
 
 
@@ -149,7 +199,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--channels", type=int, default=CHANNELS_PER_GPU, help="channels per GPU")
+    ap.add_argument("--workload", default="dmr", choices=sorted(WORKLOADS),
+                    help="dmr = the bench line (BASELINE configs[1]); the others run the same harness on another pipe")
+    ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: the workload's)")
     ap.add_argument("--samples", type=int, default=SAMPLES_PER_STEP, help="samples per channel per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
@@ -158,13 +210,17 @@ def main():
                     help="device arm: three kernels back to back on one stream instead of cross-step pipelining")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    wl = WORKLOADS[args.workload]
+    if args.channels is None:
+        args.channels = wl["channels"]
+    metric = METRIC if args.workload == "dmr" else "Msamples/s %s pipe" % args.workload.upper()
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cores = os.cpu_count() or 1
-    config = {"workload": "%d ch/GPU x %d samples/step synthetic 48 kHz 4-FSK DMR (BASELINE configs[1]): "
-                          "WideRrcFilter -> GfskDemodulator(10) -> Dmr::Decoder" % (args.channels, args.samples),
+    config = {"workload": "%d ch/GPU x %d samples/step synthetic 48 kHz %s: %s" % (
+                  args.channels, args.samples, args.workload.upper(), wl["desc"]),
               "channels_per_gpu": args.channels, "samples_per_channel_per_step": args.samples,
               "l2": "inputs larger than L2 (%.0f MB/step/GPU)" % (args.channels * args.samples * 4 / 1e6),
               "sharding": "contiguous channel ranges per rank, no data-path collective"}
@@ -175,9 +231,10 @@ def main():
         # bounded sample: enough channels for a few seconds of work on all cores
         args.warmup_ref, args.steps_ref = min(args.warmup, 1), max(1, min(args.steps, 3))
         nch = min(args.channels, 64 * cores)
-        x = build_host_sample(nch, args.samples, seed=1234)
+        x = build_host_sample(args.workload, nch, args.samples, seed=1234)
+        args.orc_proto = proto_ids(args.workload)[1]
         val, kind, sample, sec = reference_arm(args, x, cores)
-        line = {"metric": METRIC, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps_ref,
+        line = {"metric": metric, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps_ref,
                 "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
@@ -205,8 +262,9 @@ def main():
             dist.barrier()
 
     C, L = args.channels, args.samples
-    x, _ = synth.dmr_channel_bank(C, L, seed=1234 + rank, device=dev)      # [C, pitch] float32 in HBM
-    pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=L, device=dev)
+    dh_proto, orc_proto = proto_ids(args.workload)
+    x = workload_signal(args.workload, C, L, 1234 + rank, dev)             # [C, pitch] float32 in HBM
+    pipe = dh.Pipe(C, dh_proto, max_chunk=L, device=dev)
     stream = torch.cuda.current_stream()
 
     sampler = ClockSampler(local_rank)
@@ -214,7 +272,8 @@ def main():
     # cross-step software pipelining (dh_pipe_set_async): K1 of step i+1 overlaps K2 + decoder of step i on two
     # internal streams; every kernel of all K steps still runs inside the timed region (joined by pipe.sync)
     pipe.set_async(not args.no_async)
-    config["pipelining"] = "none" if args.no_async else "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)"
+    config["pipelining"] = ("none" if args.no_async or wl["dominant"] != 0 else
+                            "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)")
     for _ in range(args.warmup):
         pipe.process(x, n=L)
         pipe.discard()
@@ -361,30 +420,35 @@ def main():
     # ---- roofline of the dominant kernel (K1) ------------------------------------------------------------------
     peak, peak_src = peaks()
     # stage sums cover every (sub-)chunk launch of the timed region; per step = / steps
-    k1_ms = stage_ms[0] / args.steps
-    achieved = C * L * ALGO_BYTES_PER_SAMPLE_K1 / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    dom = wl["dominant"]
+    algo_bytes = wl["algo"]
+    k1_ms = stage_ms[dom] / args.steps           # launch time of the dominant kernel (K1, or K2 for the FSK pipes)
+    achieved = C * L * algo_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
-        if tj.get("channels") == C and tj.get("samples") == L:
+        if tj.get("channels") == C and tj.get("samples") == L and args.workload == "dmr":
             traffic = tj.get("dram_bytes_per_launch")
     iso = None
     if iso_calls:
-        iso_k1 = iso_ms[0] / iso_calls
-        iso_ach = C * L * ALGO_BYTES_PER_SAMPLE_K1 / (iso_k1 * 1e-3) / 1e9
+        iso_k1 = iso_ms[dom] / iso_calls
+        iso_ach = C * L * algo_bytes / (iso_k1 * 1e-3) / 1e9
         iso = {"ms_per_launch": iso_k1, "achieved": iso_ach, "frac": iso_ach / peak, "launches": iso_calls,
-               "stage_ms_per_step": {"k1_rrc": iso_k1, "k2_demod": iso_ms[1] / iso_calls, "k3_k4_dmr": iso_ms[2] / iso_calls},
+               "stage_ms_per_step": {"k1_rrc": iso_ms[0] / iso_calls, "k2_demod": iso_ms[1] / iso_calls,
+                                     "k3_k4_dmr": iso_ms[2] / iso_calls},
                "note": "same kernels, same inputs, three kernels back to back on one stream right after the timed "
                        "region: K1 with the SMs to itself.  In the timed region K1 of step i+1 shares the SMs with K2/K3 "
                        "of step i, which stretches its launch duration while shortening the step"}
-    roofline = {"bound": "hbm", "kernel": "rrc_fir_kernel<80> (K1)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    kernel_name = {"dmr": "rrc_fir_kernel<80> (K1)", "ysf": "rrc_fir_kernel<80> (K1)", "nxdn": "rrc_fir_kernel<160> (K1)",
+                   "dstar": "demod_kernel<10,10> (K2)", "pocsag": "demod_kernel<10,40> (K2)"}[args.workload]
+    roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "not_overlapped": iso,
-                "algorithmic_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_K1,
+                "algorithmic_bytes_per_sample": algo_bytes,
                 "ms_per_launch": k1_ms * args.steps / max(1, calls), "k1_ms_per_step": k1_ms,
-                "stage_ms_per_step": {"k1_rrc": k1_ms, "k2_demod": stage_ms[1] / args.steps,
+                "stage_ms_per_step": {"k1_rrc": stage_ms[0] / args.steps, "k2_demod": stage_ms[1] / args.steps,
                                       "k3_k4_dmr": stage_ms[2] / args.steps,
                                       "launches_per_stage_per_step": calls / args.steps,
                                       "note": "per-kernel CUDA events on the launching streams; with cross-step "
@@ -392,10 +456,11 @@ def main():
                                               "exceeds ms_per_step"},
                 "fp32_issue_bound": {"note": "K1 executes 162 separately rounded fp32 ops/sample (no FMA, bit-exact); "
                                              "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
-                                     "fp32_ops_per_s": C * L * 162 / (k1_ms * 1e-3) if k1_ms > 0 else None,
+                                     "fp32_ops_per_s": C * L * (322 if args.workload == "nxdn" else 162) / (k1_ms * 1e-3)
+                                     if k1_ms > 0 and dom == 0 else None,
                                      "peak_fp32_lane_ops_per_s_at_max_clock": 148 * 128 * 1.965e9},
-                "pipe_bytes_per_sample": ALGO_BYTES_PER_SAMPLE_PIPE,
-                "pipe_frac_of_hbm": value * 1e6 / world * ALGO_BYTES_PER_SAMPLE_PIPE / 1e9 / peak}
+                "pipe_bytes_per_sample": wl["pipe_bytes"],
+                "pipe_frac_of_hbm": value * 1e6 / world * wl["pipe_bytes"] / 1e9 / peak}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------
     cpu = None
@@ -405,17 +470,17 @@ def main():
             orc = oracle_lib.best()
             probe = x[:cores, :L].cpu().numpy()
             t0 = time.perf_counter()
-            orc.pipe_batch(oracle_lib.PROTO_DMR, probe, threads=cores, chunk=4096)
+            orc.pipe_batch(orc_proto, probe, threads=cores, chunk=4096)
             per_ch = (time.perf_counter() - t0) / 1.0            # seconds for `cores` channels in parallel
             nch = int(max(cores, min(C, cores * max(1.0, args.cpu_seconds / max(per_ch, 1e-3)))))
             xs = x[:nch, :L].cpu().numpy()
             t0 = time.perf_counter()
-            _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, xs, threads=cores, chunk=4096)
+            _, outs, metas = orc.pipe_batch(orc_proto, xs, threads=cores, chunk=4096, meta_cap=1 << 15)
             dt = time.perf_counter() - t0
             cpu = {"value": nch * L / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": orc.kind,
                    "sample": "first %d of %d channels x %d samples (one step's batch), %.1f s" % (nch, C, L, dt)}
             # the same sample doubles as an in-run parity check of the GPU path
-            chk = dh.Pipe(nch, dh.PROTO_DMR, max_chunk=L, device=dev)
+            chk = dh.Pipe(nch, dh_proto, max_chunk=L, device=dev)
             chk.process(x[:nch], n=L)
             chk.collect()
             ok = all(chk.output(c) == outs[c].tobytes() and chk.meta(c) == metas[c] for c in range(nch))
@@ -424,7 +489,7 @@ def main():
         except Exception as ex:   # the checker is optional for the measurement itself
             cpu = {"value": None, "unit": "Msamples/s", "cores": cores, "kind": "unavailable", "sample": str(ex)}
 
-    line = {"metric": METRIC, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+    line = {"metric": metric, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}

@@ -111,16 +111,18 @@ def test_rrc_many_channels_linearity_property():
     bank.close()
 
 
-def test_rrc_custom_taps_and_argument_errors():
+@pytest.mark.parametrize("nz,chunks", [(32, [1000, 2000]), (160, [2999, 1]), (164, [3000]), (200, [7, 1493, 1500]),
+                                       (1024, [2500, 500])])
+def test_rrc_custom_taps_and_argument_errors(nz, chunks):
+    """custom filters: taps in the kernel parameter block (<= 164 taps) or staged in shared memory (longer)"""
     import digiham_b200 as dh
     rng = np.random.default_rng(11)
-    nz = 32
     coeffs = rng.normal(size=nz + 1).astype(np.float32)
     gain = 3.7
     n = 3000
     x = rng.uniform(-1, 1, size=(2, n)).astype(np.float32)
     bank = dh.RrcBank(2, custom=(nz, gain, coeffs))
-    y = _run_gpu(bank, x, [1000, 2000])
+    y = _run_gpu(bank, x, chunks)
     # numpy restatement of src/rrc_filter/rrc_filter.cpp:22-34 for arbitrary taps
     for c in range(2):
         xp = np.concatenate([np.zeros(nz, np.float32), x[c]])
