@@ -242,6 +242,53 @@ def test_dstar_meta_replay_lines():
     assert lines[5:] == ["protocol:DSTAR", ""]
 
 
+CRC_SRC = r"""
+#define __host__
+#define __device__
+#include "crc_par.cuh"
+#include <cstdio>
+#include <cstdint>
+#include <random>
+using namespace dh;
+template <int KIND, int N> unsigned long long check() {
+    constexpr CrcTable<N> t = make_crc_table<KIND, N>();
+    std::mt19937_64 rng(KIND * 1000 + N);
+    unsigned long long bad = 0;
+    for (int trial = 0; trial < 20000; trial++) {
+        unsigned char bits[N];
+        for (int i = 0; i < N; i++) bits[i] = (trial < 2 ? trial : (rng() >> 17)) & 1;
+        // the reference's bit-serial update (crc16.c:3-19 / sacch.cpp:76-90 / facch1.cpp:60-75)
+        uint32_t crc = KIND == 0 ? 0u : (KIND == 1 ? 0x3Fu : 0xFFFu);
+        for (int i = 0; i < N; i++)
+            crc = KIND == 0 ? crc_step_ysf16(crc, bits[i]) : (KIND == 1 ? crc_step_nxdn6(crc, bits[i]) : crc_step_nxdn12(crc, bits[i]));
+        if (KIND == 0) crc ^= 0xFFFFu;
+        uint32_t par = t.c;
+        for (int i = 0; i < N; i++) if (bits[i]) par ^= t.t[i];
+        if (par != crc) bad++;
+    }
+    return bad;
+}
+int main() {
+    unsigned long long bad = check<0, 32>() + check<0, 80>() + check<0, 160>() + check<1, 26>() + check<2, 80>();
+    printf("%llu\n", bad);
+    return 0;
+}
+"""
+
+
+def test_parallel_crc_tables_equal_bit_serial_crc():
+    """crc_par.cuh: the compile-time affine tables used by the YSF / NXDN kernels reproduce the bit-serial CRCs of the
+    reference for random messages of every length in use (host build of the same header)."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "crc.cpp")
+        open(src, "w").write(CRC_SRC)
+        exe = os.path.join(d, "crc")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fconstexpr-ops-limit=200000000", "-fconstexpr-loop-limit=1000000",
+                        "-I" + os.path.join(ROOT, "digiham_b200", "csrc"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert int(out.strip()) == 0
+
+
 def test_synthetic_generators_are_deterministic():
     from digiham_b200 import synth
     a = synth.dmr_symbols(20, seed=3)
