@@ -421,6 +421,8 @@ def main():
         frames = [pipe.output(c) for c in range(C)]
         metas = [pipe.meta(c) for c in range(C)]
         pipe.decoder.clear()
+        shard.gather_frames(frames[:8] + [b""] * (C - 8), world * C, device=dev)   # connection set-up is not the gather
+        torch.cuda.synchronize()
         barrier()
         t0 = time.perf_counter()
         gf = shard.gather_frames(frames, world * C, device=dev)
