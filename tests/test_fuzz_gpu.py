@@ -1,0 +1,19 @@
+"""Randomised differential test (tools/fuzz_parity.py): every pipe vs the CPU oracle with random channel counts,
+lengths, chunkings (blocking and asynchronous mode), impairments and error rates.  A short budget here; the long
+runs of the round are recorded in profiles/r01_fuzz.txt."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+import oracle_lib
+
+pytestmark = pytest.mark.gpu
+
+
+def test_fuzz_all_pipes_short():
+    tool = os.path.join(oracle_lib.ROOT, "tools", "fuzz_parity.py")
+    r = subprocess.run([sys.executable, tool, "20", "3"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "fuzz: all equal" in r.stdout
