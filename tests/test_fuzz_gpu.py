@@ -17,3 +17,10 @@ def test_fuzz_all_pipes_short():
     r = subprocess.run([sys.executable, tool, "20", "3"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
     assert r.returncode == 0, r.stdout[-2000:]
     assert "fuzz: all equal" in r.stdout
+
+
+def test_fuzz_decoders_short():
+    tool = os.path.join(oracle_lib.ROOT, "tools", "fuzz_decoders.py")
+    r = subprocess.run([sys.executable, tool, "15", "4"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+    assert r.returncode == 0, r.stdout[-2000:]
+    assert "decoder fuzz: all equal" in r.stdout
