@@ -186,3 +186,18 @@ def test_pipe_full_size_properties():
     _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, xc, threads=8)
     for ch in range(8):
         assert a[ch][1] == outs[ch].tobytes() and a[ch][2] == metas[ch], ch
+
+
+def test_pipe_config1_ten_seconds_single_call():
+    """BASELINE configs[0] shape: one channel, 10 s (480000 samples) in ONE call, plus two more channels beside it."""
+    import digiham_b200 as dh
+    C, n = 3, 480000
+    x, _ = synth.dmr_channel_bank(C, n, seed=23, device="cuda", noise_fraction=0.0)
+    pipe = dh.Pipe(C, dh.PROTO_DMR, max_chunk=n)
+    pipe.process(x, n=n)
+    pipe.collect()
+    _, outs, metas = oracle_lib.best().pipe_batch(oracle_lib.PROTO_DMR, x[:, :n].cpu().numpy(), threads=3, meta_cap=1 << 16)
+    for ch in range(C):
+        assert pipe.output(ch) == outs[ch].tobytes() and pipe.meta(ch) == metas[ch], ch
+    assert sum(len(o) for o in outs) > 27 * 100
+    pipe.close()
