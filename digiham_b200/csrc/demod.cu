@@ -593,6 +593,9 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     p.samples_cap = (kBlockSyms * h->sps + 2 + 3 + 3 + 3) & ~3;
     // samples | var (doubles; 8-byte aligned because samples_cap is a multiple of 4)
     p.group_floats = p.samples_cap + 2 * ((h->sps + 1) & ~1);
+    // Three 10-lane groups of a warp read 10 consecutive floats each in the variance search: with group segments
+    // that are 12 banks apart (mod 32) their bank ranges do not overlap (even, so the doubles stay 8-byte aligned)
+    if (h->sps == 10 || h->sps == 20) p.group_floats += (12 - p.group_floats % 32 + 32) % 32;
 
     // lanes per channel: 10 on the compile-time fast paths (3 channels per warp), else 16 or 32
     const bool fast = (h->sps == 10 || h->sps == 20 || h->sps == 40) && h->lo == eval_lo(h->sps) && h->hi == eval_hi(h->sps);
