@@ -5,7 +5,7 @@
 //     sum = 0.0f; for i in 0..nZeros: sum = fl32(sum + fl32(c[i] * x[t - nZeros + i]));  out = fl32(fl64(sum) / gain)
 // i.e. separately rounded products and a strictly ordered float32 accumulation (the x86-64 reference build has
 // no FMA), then one double division rounded to float.  For the two built-in gains the division is replaced by a
-// multiplication with the correctly rounded reciprocal: tests/test_rrc_host.py proves, by exhaustion over all
+// multiplication with the correctly rounded reciprocal: tests/test_host_logic.py (test_reciprocal_gain_exhaustive) proves, by exhaustion over all
 // 2^32 float inputs, that fl32(fl64(s) * fl64(1/g)) == fl32(fl64(s) / g) for g in {8.337797030, 16.67711971}.
 //
 // Kernel shape (1-D convolution, FP32-issue bound at 2*(nZeros+1) flop per sample — no tensor cores):
