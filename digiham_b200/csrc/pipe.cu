@@ -244,6 +244,7 @@ int dh_pipe_set_async(dh_pipe* h, int enable, void* stream) {
         if (rc != DH_OK) return rc;
     }
     h->async_mode = enable != 0;
+    if (h->rrc) return dh_rrc_set_tile_preference(h->rrc, h->async_mode ? 1 : 0);
     return DH_OK;
 }
 

@@ -85,6 +85,9 @@ DH_API int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* 
 /* Host-buffer variant (synchronous): h_in/h_out are [channels][pitch] in host memory; staging is internal. */
 DH_API int dh_rrc_process_host(dh_rrc* h, uint32_t channels, const float* h_in, size_t in_pitch, float* h_out,
                                size_t out_pitch, size_t n);
+/* Tile-size policy of the FIR kernel: 0 (default) = fastest stand-alone; 1 = favour the smaller register footprint,
+ * which is faster when other kernels share the SMs (set by dh_pipe_set_async). */
+DH_API int dh_rrc_set_tile_preference(dh_rrc* h, int prefer_small);
 DH_API int dh_rrc_reset(dh_rrc* h, void* stream);
 DH_API void dh_rrc_destroy(dh_rrc* h);
 
