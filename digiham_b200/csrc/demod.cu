@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
                 float sum = 0.0f, vsum = 0.0f;
                 if (SPS > 0) {
                     constexpr int kLo = eval_lo(SPS > 0 ? SPS : 10), kHi = eval_hi(SPS > 0 ? SPS : 10);
-                    if (SPS == 40) {
+                    if (SPS == 40 || (SPS == 20 && G == 20)) {
                         // Wide symbols: the lanes' windows are 200 floats apart (8 banks), so scalar loads collide five
                         // ways.  The windows share the same offset r inside a 16-byte unit ((a0 + vo) & 3; only symbol 0
                         // of a block, which is not shifted by the pending nudge, may differ), so they are fetched as 11
@@ -286,9 +286,10 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
                         // instructions and 2.5 x fewer wavefronts (3.34 -> 2.4 ms per 32768-channel launch).
                         const int r = (a0 + (j ? vo : 0)) & 3;
                         const float4* wa = reinterpret_cast<const float4*>(w - r);
-                        float x[44];
+                        constexpr int NV = (SPS + 6) / 4;   // vectors that cover r + SPS floats for every r <= 3
+                        float x[4 * NV];
 #pragma unroll
-                        for (int v4 = 0; v4 < 11; v4++) {
+                        for (int v4 = 0; v4 < NV; v4++) {
                             const float4 t = wa[v4];
                             x[4 * v4] = t.x;
                             x[4 * v4 + 1] = t.y;
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ 
                         auto consume = [&](auto R) {
                             constexpr int kR = decltype(R)::value;
 #pragma unroll
-                            for (int i = 0; i < 40; i++) {
+                            for (int i = 0; i < SPS; i++) {
                                 const float v = x[i + kR];
                                 if (i >= kLo && i < kHi) sum = __fadd_rn(sum, v);
                                 vsum = __fadd_rn(vsum, v);
@@ -637,7 +638,9 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     // latency of a block halves: 3.99 -> 3.50 ms per 32768-channel step (a full warp per channel: 7.6 ms).
     // DH_DEMOD_G40 = 10 selects the narrow variant (experiments).
     static const int g40 = getenv("DH_DEMOD_G40") ? atoi(getenv("DH_DEMOD_G40")) : 20;
-    const int G = fast ? (h->sps == 40 && g40 != 10 ? 20 : 10) : (h->sps <= 16 ? 16 : 32);
+    // sps = 20 likewise: 20-lane groups (one variance pass, vector window loads): NXDN pipe 2.43 -> 2.30 ms per step.
+    static const int g20 = getenv("DH_DEMOD_G20") ? atoi(getenv("DH_DEMOD_G20")) : 20;
+    const int G = fast ? ((h->sps == 40 && g40 != 10) || (h->sps == 20 && g20 == 20) ? 20 : 10) : (h->sps <= 16 ? 16 : 32);
     const int threads = fast && h->sps == 40 && G == 10 ? 32 : kThreads;
     const int groups = (threads / 32) * (32 / G);
     const unsigned grid = (h->channels + groups - 1) / groups;
@@ -651,6 +654,8 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         DH_LAUNCH_DEMOD(10, 10, kThreads);
     } else if (G == 10 && h->sps == 20) {
         DH_LAUNCH_DEMOD(10, 20, kThreads);
+    } else if (G == 20 && h->sps == 20) {
+        DH_LAUNCH_DEMOD(20, 20, kThreads);
     } else if (G == 20) {
         DH_LAUNCH_DEMOD(20, 40, kThreads);
 
