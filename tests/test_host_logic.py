@@ -289,6 +289,16 @@ def test_parallel_crc_tables_equal_bit_serial_crc():
     assert int(out.strip()) == 0
 
 
+def test_headers_compile_without_a_gpu():
+    """include/digiham_b200.h is plain C99; the header-compatible C++ facades compile against the csdr shim."""
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", "-x", "c",
+                    os.path.join(inc, "digiham_b200.h")], check=True)
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-fsyntax-only", "-I" + inc,
+                    "-I" + os.path.join(ROOT, "oracle", "csdr_shim"), os.path.join(ROOT, "tests", "cpp", "facade_pipe.cpp")],
+                   check=True)
+
+
 def test_synthetic_generators_are_deterministic():
     from digiham_b200 import synth
     a = synth.dmr_symbols(20, seed=3)
