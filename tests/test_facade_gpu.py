@@ -93,3 +93,15 @@ def test_facade_rrc_and_dvf(harness):
     a = rng.integers(-20000, 20000, 4000).astype(np.int16)
     out, _ = _run(harness, "dvf", a)
     assert np.array_equal(out.view(np.int16), oracle_lib.best().dvf(a, chunk=128))
+
+
+def test_c_abi_example_program(tmp_path):
+    """examples/many_channels.cpp: the streaming C-ABI call sequence of INTEGRATION.md compiles, runs and decodes."""
+    exe = str(tmp_path / "many_channels")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(ROOT, "examples", "many_channels.cpp"), "-L" + os.path.join(ROOT, "digiham_b200"),
+                    "-ldigiham_b200", "-Wl,-rpath," + os.path.join(ROOT, "digiham_b200"), "-L/usr/local/cuda/lib64",
+                    "-lcudart", "-o", exe], check=True)
+    r = subprocess.run([exe, "64", "3"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "64 channels x 3 steps" in r.stdout
