@@ -90,6 +90,9 @@ int decoder_reserve(dh_decoder* h, size_t max_syms) {
     for (int set = 0; set < 2; set++) {
         DH_CUDA(cudaMalloc(&h->d_out_set[set], (size_t) h->channels * h->out_cap));
         DH_CUDA(cudaMalloc(&h->d_ev_set[set], (size_t) h->channels * h->ev_cap * sizeof(DecEvent)));
+        // collect copies the widest channel's byte count for every channel: keep the unused tails defined
+        DH_CUDA(cudaMemset(h->d_out_set[set], 0, (size_t) h->channels * h->out_cap));
+        DH_CUDA(cudaMemset(h->d_ev_set[set], 0, (size_t) h->channels * h->ev_cap * sizeof(DecEvent)));
     }
     return DH_OK;
 }
