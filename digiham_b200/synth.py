@@ -833,7 +833,7 @@ def dstar_dprs(payload="DL1ABC-7>API282,DSTAR*:!4807.03N/01131.00E>B200 test"):
     return "$$CRC%04X,%s" % (dstar_crc(body.encode("latin-1")), body)
 
 
-def dstar_symbols(n_frames, seed=0, lead_in=None, bit_errors=0.0):
+def dstar_symbols(n_frames, seed=0, lead_in=None, bit_errors=0.0, gga=True):
     """D-Star traffic: transmissions with radio header (voice, some data headers, some with a broken CRC), voice
     frames carrying slow data (20-character message, header resend, DPRS and NMEA GGA sentences, filler), late
     entry (voice sync without header), terminators (full and second half only), noise gaps."""
@@ -861,9 +861,13 @@ def dstar_symbols(n_frames, seed=0, lead_in=None, bit_errors=0.0):
             blocks += dstar_slow_data_blocks(message="B200 msg %d %s" % (made, my))
         if r > 0.3:
             blocks += dstar_slow_data_blocks(header41=hdr)
+        # gga=False keeps the random draws but leaves the sentence out: the REFERENCE aborts (std::stof throws) on a
+        # GGA sentence whose fields were corrupted by bit errors while its 8-bit checksum still matches
         if rng.random() < 0.6:
-            blocks += dstar_slow_data_blocks(text=dstar_gga(lat=float(rng.uniform(0, 8959)), lon=float(rng.uniform(0, 17959)),
-                                                            south=bool(rng.integers(0, 2)), west=bool(rng.integers(0, 2))))
+            gga_blocks = dstar_slow_data_blocks(text=dstar_gga(lat=float(rng.uniform(0, 8959)), lon=float(rng.uniform(0, 17959)),
+                                                               south=bool(rng.integers(0, 2)), west=bool(rng.integers(0, 2))))
+            if gga:
+                blocks += gga_blocks
         if rng.random() < 0.6:
             blocks += dstar_slow_data_blocks(text=dstar_dprs("%s>API282,DSTAR*:!4807.03N/01131.00E>run %d" % (my, made)))
         filler = bytes([0x66] * 6)

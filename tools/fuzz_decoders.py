@@ -1,5 +1,5 @@
 """Randomised differential test of the decoder banks on SYMBOL streams: spliced valid traffic, truncated frames,
-noise, bare sync words at random places, random chunking.  usage: fuzz_decoders.py [seconds] [seed]"""
+noise, bare sync words at random places, random chunking.  usage: fuzz_decoders.py [seconds] [seed] [max_rounds]   (max_rounds makes the run deterministic)"""
 import os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -12,6 +12,8 @@ import oracle_lib
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 60.0
 seed0 = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+max_rounds = int(sys.argv[3]) if len(sys.argv) > 3 else 1 << 30
+rounds = 0
 orc = oracle_lib.best()
 rng = np.random.default_rng(seed0)
 
@@ -26,7 +28,7 @@ PROTOS = {
     "nxdn": (dh.PROTO_NXDN, oracle_lib.PROTO_NXDN, 4,
              lambda k: synth.nxdn_symbols(10, seed=k, symbol_errors=[0, 0.01, 0.05][k % 3]), [synth.NXDN_FSW]),
     "dstar": (dh.PROTO_DSTAR, oracle_lib.PROTO_DSTAR, 2,
-              lambda k: synth.dstar_symbols(40, seed=k, bit_errors=[0, 0.003, 0.02][k % 3]),
+              lambda k: synth.dstar_symbols(40, seed=k, bit_errors=[0, 0.003, 0.02][k % 3], gga=(k % 3 == 0)),
               [synth.DSTAR_HEADER_SYNC, synth.DSTAR_VOICE_SYNC, synth.DSTAR_TERMINATOR, synth.DSTAR_TERMINATOR[24:]]),
     "pocsag": (dh.PROTO_POCSAG, oracle_lib.PROTO_POCSAG, 2,
                lambda k: synth.pocsag_bits([(9 + k, 3, "DEC FUZZ %d" % k)], seed=k, bit_errors=k % 4, preamble=64 + (k % 7) * 32),
@@ -87,8 +89,11 @@ while time.time() < t_end and not bad:
             stats[name][1] += ro.size + len(rm)
         stats[name][0] += C
         bank.close()
-        if bad or time.time() > t_end:
+        rounds += 1
+        if bad or time.time() > t_end or rounds >= max_rounds:
             break
+    if rounds >= max_rounds:
+        break
 for k, v in stats.items():
     print("%-7s channels %6d  bytes compared %9d" % (k, v[0], v[1]))
 print("decoder fuzz: %s" % ("FAILED" if bad else "all equal"))
