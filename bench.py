@@ -481,7 +481,12 @@ def main():
                                              "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
                                      "fp32_ops_per_s": C * L * (322 if args.workload == "nxdn" else 162) / (k1_ms * 1e-3)
                                      if k1_ms > 0 and dom == 0 else None,
-                                     "peak_fp32_lane_ops_per_s_at_max_clock": 148 * 128 * 1.965e9},
+                                     "peak_fp32_lane_ops_per_s_at_max_clock": 148 * 128 * 1.965e9,
+                                     "frac_in_region": (C * L * (322 if args.workload == "nxdn" else 162) / (k1_ms * 1e-3)
+                                                        / (148 * 128 * 1.965e9)) if k1_ms > 0 and dom == 0 else None,
+                                     "frac_not_overlapped": (C * L * (322 if args.workload == "nxdn" else 162)
+                                                             / (iso["ms_per_launch"] * 1e-3) / (148 * 128 * 1.965e9))
+                                     if iso and dom == 0 else None},
                 "pipe_bytes_per_sample": wl["pipe_bytes"],
                 "pipe_frac_of_hbm": value * 1e6 / world * wl["pipe_bytes"] / 1e9 / peak}
 
