@@ -163,7 +163,11 @@ __device__ void collect_sacch(NCtx& c, uint32_t word) {
     NxdnState& s = c.st;
     const int index = (int) ((word >> 30) ^ 3u);
     if (index > 0 && !((s.sacch_mask >> (index - 1)) & 1)) return;   // fragment before it is missing
-    s.sacch[index] = (word >> 6) & 0x3FFFFu;                          // bits 8..25
+    const uint32_t fragment = (word >> 6) & 0x3FFFFu;                  // bits 8..25
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (k == index) s.sacch[k] = fragment;                         // static indices: the state stays in registers
+    }
     s.sacch_mask |= 1 << index;
     if (s.sacch_mask != 0xF) return;
     // 72 bits = 4 x 18, MSB first; only bytes 0, 2, 3..6 are read (sacch.cpp:140-154)
