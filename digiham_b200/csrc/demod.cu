@@ -13,12 +13,15 @@
 //     mixed float/double arithmetic, slice.
 //
 // GPU shape: the only sequential dependency is the +-1 nudge from one 100-symbol block to the next, so a group of
-// G lanes (half a warp at sps <= 16, a full warp otherwise) owns one channel and walks its blocks in order.
-// Inside a block the window positions are known up front: lanes own symbols for the window sums, then the ring
-// min/max becomes (prefix over this block) x (suffix over the previous block) computed with __shfl_up_sync scans,
-// then lanes own sample phases for the variance search.  Samples are staged block-wise into shared memory with
-// aligned float4 loads.  Partially filled blocks are carried: the unconsumed tail of every channel is moved to the
-// front of its work row, right-aligned against the position where the producer writes the next chunk.
+// G lanes owns one channel and walks its blocks in order: G = 10 at sps 10 (three channels per warp, compile-time
+// fast path), G = 20 at sps 20 / 40 (fast paths with 128-bit window loads), G = 16 / 32 for any other sps (generic
+// kernel).  Inside a block the window positions are known up front: lanes own symbols for the window sums, then
+// the ring min/max becomes (prefix over this block) x (suffix over the previous block) computed with shuffle
+// scans, then lanes own sample phases for the variance search.  Samples are staged block-wise into shared memory
+// with 16-byte cp.async copies — from the bank's own work row (a producer kernel wrote the chunk there) or straight
+// from the caller's rows (DemodParams::ext).  Partially filled blocks are carried: the unconsumed tail of every
+// channel is moved right-aligned in front of the position where the next chunk starts, in the other of two
+// alternating work-row sets.
 #include "common.cuh"
 
 #include <cfloat>
