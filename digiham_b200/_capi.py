@@ -9,6 +9,8 @@ _LIB_NAME = "libdigiham_b200.so"
 
 RRC_WIDE = 0
 RRC_NARROW = 1
+FMT_F32, FMT_S16 = 0, 1
+SHARD_SCATTER = 1
 PROTO_DMR, PROTO_YSF, PROTO_POCSAG, PROTO_NXDN, PROTO_DSTAR = 0, 1, 2, 3, 4
 
 
@@ -100,6 +102,42 @@ def lib():
     L.dh_decoder_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
     L.dh_pipe_destroy.restype = None
+    L.dh_rrc_process_s16.argtypes = L.dh_rrc_process.argtypes
+    L.dh_pipe_process_device_s16.argtypes = L.dh_pipe_process_device.argtypes
+    L.dh_pipe_process_host_s16.argtypes = L.dh_pipe_process_host.argtypes
+    L.dh_pipe_submit_host_s16.argtypes = L.dh_pipe_submit_host.argtypes
+    L.dh_pipe_host_pitch_s16.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_host_pitch_s16.restype = ctypes.c_size_t
+    L.dh_pipe_input_event.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    for name in ("dh_rrc_channels", "dh_demod_channels", "dh_decoder_channels", "dh_dvf_channels", "dh_pipe_channels"):
+        getattr(L, name).argtypes = [ctypes.c_void_p]
+        getattr(L, name).restype = ctypes.c_uint32
+    c_u64_p = ctypes.POINTER(ctypes.c_uint64)
+    L.dh_shard_unique_id.argtypes = [ctypes.c_void_p]
+    L.dh_shard_comm_init.argtypes = [c_void_pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.dh_shard_comm_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_shard_channel_range.argtypes = [ctypes.c_uint64, ctypes.c_int, ctypes.c_int, c_u64_p, c_u64_p]
+    L.dh_shard_wire_layout.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32),
+                                       ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_shard_create.argtypes = [c_void_pp, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_uint64, ctypes.c_int, ctypes.c_size_t, ctypes.c_int]
+    L.dh_shard_pitch.argtypes = [ctypes.c_void_p]
+    L.dh_shard_pitch.restype = ctypes.c_size_t
+    L.dh_shard_local_channels.argtypes = [ctypes.c_void_p]
+    L.dh_shard_local_channels.restype = ctypes.c_uint32
+    L.dh_shard_pipe.argtypes = [ctypes.c_void_p]
+    L.dh_shard_pipe.restype = ctypes.c_void_p
+    L.dh_shard_submit_device.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                         ctypes.c_void_p]
+    L.dh_shard_collect_step.argtypes = [ctypes.c_void_p]
+    L.dh_shard_discard_step.argtypes = [ctypes.c_void_p]
+    L.dh_shard_sync.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_shard_output.argtypes = [ctypes.c_void_p, ctypes.c_uint64, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_shard_meta.argtypes = [ctypes.c_void_p, ctypes.c_uint64, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
+    L.dh_shard_clear.argtypes = [ctypes.c_void_p]
+    L.dh_shard_stats.argtypes = [ctypes.c_void_p, c_u64_p, c_u64_p, c_u64_p]
+    L.dh_shard_destroy.argtypes = [ctypes.c_void_p]
+    L.dh_shard_destroy.restype = None
     L.dh_dvf_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32]
     L.dh_dvf_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_size_t,
                                  ctypes.c_size_t, ctypes.c_void_p]
@@ -148,15 +186,16 @@ class RrcBank:
                                              float(gain), c.ctypes.data))
 
     def process(self, x, out=None, n=None, stream=None):
-        """x: float32 CUDA tensor [channels, pitch]; filters the first n samples of every row."""
-        assert x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] == self.channels
+        """x: float32 (or int16: fused `csdr convert -i s16 -o float`) CUDA tensor [channels, pitch]; filters the
+        first n samples of every row."""
+        assert x.is_cuda and x.dtype in (torch.float32, torch.int16) and x.dim() == 2 and x.shape[0] == self.channels
         assert x.stride(1) == 1
         if n is None:
             n = x.shape[1]
         if out is None:
             out = torch.empty((self.channels, pitch4(n)), dtype=torch.float32, device=x.device)
-        check(lib().dh_rrc_process(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n,
-                                   _stream_ptr(stream)))
+        fn = lib().dh_rrc_process_s16 if x.dtype == torch.int16 else lib().dh_rrc_process
+        check(fn(self._h, x.data_ptr(), x.stride(0), out.data_ptr(), out.stride(0), n, _stream_ptr(stream)))
         return out
 
     def reset(self, stream=None):
@@ -329,25 +368,35 @@ class Pipe:
     def host_pitch(self):
         return lib().dh_pipe_host_pitch(self._h)
 
+    @property
+    def host_pitch_s16(self):
+        return lib().dh_pipe_host_pitch_s16(self._h)
+
     def process(self, x, n=None, stream=None):
-        """x: float32 tensor [channels, pitch]; CUDA tensors are consumed in place, CPU tensors are copied."""
-        assert x.dtype == torch.float32 and x.dim() == 2 and x.shape[0] == self.channels and x.stride(1) == 1
+        """x: float32 or int16 tensor [channels, pitch]; CUDA tensors are consumed in place, CPU tensors are copied."""
+        assert x.dtype in (torch.float32, torch.int16) and x.dim() == 2 and x.shape[0] == self.channels
+        assert x.stride(1) == 1
         if n is None:
             n = x.shape[1]
+        s16 = x.dtype == torch.int16
+        L = lib()
         if x.is_cuda:
-            check(lib().dh_pipe_process_device(self._h, x.data_ptr(), x.stride(0), n, _stream_ptr(stream)))
+            fn = L.dh_pipe_process_device_s16 if s16 else L.dh_pipe_process_device
         else:
-            check(lib().dh_pipe_process_host(self._h, x.data_ptr(), x.stride(0), n, _stream_ptr(stream)))
+            fn = L.dh_pipe_process_host_s16 if s16 else L.dh_pipe_process_host
+        check(fn(self._h, x.data_ptr(), x.stride(0), n, _stream_ptr(stream)))
 
     def collect(self, stream=None):
         check(lib().dh_pipe_collect(self._h, _stream_ptr(stream)))
 
     def submit(self, x, n=None):
         """Streaming interface: asynchronous upload + kernels of one block from PINNED host memory."""
-        assert (not x.is_cuda) and x.is_pinned() and x.dtype == torch.float32 and x.shape[0] == self.channels
+        assert (not x.is_cuda) and x.is_pinned() and x.dtype in (torch.float32, torch.int16)
+        assert x.shape[0] == self.channels
         if n is None:
             n = x.shape[1]
-        check(lib().dh_pipe_submit_host(self._h, x.data_ptr(), x.stride(0), n))
+        fn = lib().dh_pipe_submit_host_s16 if x.dtype == torch.int16 else lib().dh_pipe_submit_host
+        check(fn(self._h, x.data_ptr(), x.stride(0), n))
 
     def collect_step(self):
         """Waits for the oldest submitted step and appends its results to the per-channel host buffers."""

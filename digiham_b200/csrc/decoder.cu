@@ -38,18 +38,7 @@ struct dh_decoder {
     std::vector<uint8_t> h_slot_filter;
     bool filter_dirty = true;
 
-    uint32_t* h_counts = nullptr;      // pinned, [3][channels]
-    uint8_t* h_out = nullptr;          // pinned staging, grown on demand
-    size_t h_out_bytes = 0;
-    DecEvent* h_ev = nullptr;
-    size_t h_ev_bytes = 0;
-
-    std::vector<dh::ChannelResult> results;
-    std::vector<dh::MetaReplay*> replay;
-    uint64_t total_bytes = 0;
-    uint64_t total_meta = 0;
-    uint64_t total_events = 0;
-    uint64_t total_d2h = 0;   // bytes copied device->host by collect
+    dh::ResultSink sink;               // host side: per-channel results + metadata replay
 };
 
 namespace {
@@ -97,87 +86,15 @@ int decoder_reserve(dh_decoder* h, size_t max_syms) {
     return DH_OK;
 }
 
-int grow_pinned(void** p, size_t* have, size_t need) {
-    if (need <= *have) return DH_OK;
-    if (*p) cudaFreeHost(*p);
-    *p = nullptr;
-    *have = 0;
-    need = need + need / 2 + 4096;
-    DH_CUDA(cudaHostAlloc(p, need, cudaHostAllocDefault));
-    *have = need;
-    return DH_OK;
-}
-
 int decoder_collect(dh_decoder* h, int set, cudaStream_t st) {
     if (!h->d_out_set[set]) return DH_OK;
-    const uint32_t n = h->channels;
-    uint8_t* d_out = h->d_out_set[set];
-    DecEvent* d_ev = h->d_ev_set[set];
     uint32_t* d_counts = h->d_counts_set[set];
-    DH_CUDA(cudaMemcpyAsync(h->h_counts, d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    uint32_t any_flags = 0;
+    int rc = h->sink.ingest(d_counts, h->d_out_set[set], h->out_cap, h->d_ev_set[set], h->ev_cap, h->channels, 0, st,
+                            &any_flags);
+    if (rc != DH_OK) return rc;
+    DH_CUDA(cudaMemsetAsync(d_counts, 0, 3 * (size_t) h->channels * sizeof(uint32_t), st));
     DH_CUDA(cudaStreamSynchronize(st));
-    h->total_d2h += 3 * (uint64_t) n * sizeof(uint32_t);
-    const uint32_t* out_len = h->h_counts;
-    const uint32_t* ev_len = h->h_counts + n;
-    const uint32_t* flags = h->h_counts + 2 * (size_t) n;
-    uint32_t max_out = 0, max_ev = 0, any_flags = 0;
-    for (uint32_t c = 0; c < n; c++) {
-        max_out = std::max(max_out, out_len[c]);
-        max_ev = std::max(max_ev, ev_len[c]);
-        any_flags |= flags[c];
-    }
-    if (max_out) {
-        int rc = grow_pinned((void**) &h->h_out, &h->h_out_bytes, (size_t) n * max_out);
-        if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->h_out, max_out, d_out, h->out_cap, max_out, n, cudaMemcpyDeviceToHost, st));
-        h->total_d2h += (uint64_t) n * max_out;
-    }
-    if (max_ev) {
-        const size_t w = (size_t) max_ev * sizeof(DecEvent);
-        int rc = grow_pinned((void**) &h->h_ev, &h->h_ev_bytes, (size_t) n * w);
-        if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h->h_ev, w, d_ev, (size_t) h->ev_cap * sizeof(DecEvent), w, n,
-                                  cudaMemcpyDeviceToHost, st));
-        h->total_d2h += (uint64_t) n * w;
-    }
-    DH_CUDA(cudaMemsetAsync(d_counts, 0, 3 * (size_t) n * sizeof(uint32_t), st));
-    DH_CUDA(cudaStreamSynchronize(st));
-    // per-channel appends and metadata replay are independent: spread them over a few host threads
-    auto work = [&](uint32_t c0, uint32_t c1, uint64_t* sums) {
-        for (uint32_t c = c0; c < c1; c++) {
-            dh::ChannelResult& r = h->results[c];
-            if (out_len[c]) {
-                r.bytes.append(reinterpret_cast<const char*>(h->h_out + (size_t) c * max_out), out_len[c]);
-                sums[0] += out_len[c];
-            }
-            sums[2] += ev_len[c];
-            if (ev_len[c] && h->replay[c]) {
-                const size_t before = r.meta.size();
-                h->replay[c]->kv_sink = &r.meta_kv;
-                h->replay[c]->apply(h->h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
-                sums[1] += r.meta.size() - before;
-            }
-        }
-    };
-    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
-    if (n < 256) nthreads = 1;
-    std::vector<uint64_t> sums((size_t) nthreads * 8, 0);   // 8 slots apart: no false sharing
-    if (nthreads == 1) {
-        work(0, n, sums.data());
-    } else {
-        std::vector<std::thread> pool;
-        const uint32_t per = (n + nthreads - 1) / nthreads;
-        for (unsigned t = 0; t < nthreads; t++) {
-            const uint32_t c0 = std::min(n, t * per), c1 = std::min(n, (t + 1) * per);
-            pool.emplace_back(work, c0, c1, sums.data() + (size_t) t * 8);
-        }
-        for (auto& t : pool) t.join();
-    }
-    for (unsigned t = 0; t < nthreads; t++) {
-        h->total_bytes += sums[(size_t) t * 8];
-        h->total_meta += sums[(size_t) t * 8 + 1];
-        h->total_events += sums[(size_t) t * 8 + 2];
-    }
     DH_REQUIRE(any_flags == 0, DH_E_STATE,
                "dh_decoder_collect: device result buffers overflowed (flags 0x%x): collect after every %u process calls",
                any_flags, kAccumulate);
@@ -186,21 +103,41 @@ int decoder_collect(dh_decoder* h, int set, cudaStream_t st) {
 
 }  // namespace
 
+namespace dh {
+
+const ProtoOps* proto_ops(int proto) {
+    switch (proto) {
+        case DH_PROTO_DMR: return dmr_ops();
+        case DH_PROTO_POCSAG: return pocsag_ops();
+        case DH_PROTO_YSF: return ysf_ops();
+        case DH_PROTO_NXDN: return nxdn_ops();
+        case DH_PROTO_DSTAR: return dstar_ops();
+        default: return nullptr;
+    }
+}
+
+int decoder_view(dh_decoder* h, int set, DecoderView* view) {
+    DH_REQUIRE(h != nullptr && view != nullptr && (set == 0 || set == 1), DH_E_INVALID, "decoder_view: bad argument");
+    DH_REQUIRE(h->d_out_set[set] != nullptr, DH_E_STATE, "decoder_view: the bank has no result buffers yet (reserve first)");
+    view->out = h->d_out_set[set];
+    view->out_cap = h->out_cap;
+    view->ev = h->d_ev_set[set];
+    view->ev_cap = h->ev_cap;
+    view->counts = h->d_counts_set[set];
+    view->channels = h->channels;
+    view->max_syms = h->max_syms;
+    return DH_OK;
+}
+
+}  // namespace dh
+
 extern "C" {
 
 int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto) {
     DH_REQUIRE(out != nullptr, DH_E_INVALID, "dh_decoder_create: out is NULL");
     *out = nullptr;
     DH_REQUIRE(channels > 0, DH_E_INVALID, "dh_decoder_create: channels must be > 0");
-    const dh::ProtoOps* ops = nullptr;
-    switch (proto) {
-        case DH_PROTO_DMR: ops = dh::dmr_ops(); break;
-        case DH_PROTO_POCSAG: ops = dh::pocsag_ops(); break;
-        case DH_PROTO_YSF: ops = dh::ysf_ops(); break;
-        case DH_PROTO_NXDN: ops = dh::nxdn_ops(); break;
-        case DH_PROTO_DSTAR: ops = dh::dstar_ops(); break;
-        default: break;
-    }
+    const dh::ProtoOps* ops = dh::proto_ops(proto);
     DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "dh_decoder_create: protocol %d not supported", proto);
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -217,10 +154,9 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
     h->proto = proto;
     h->ops = ops;
     h->h_slot_filter.assign(channels, 3);
-    h->results.resize(channels);
-    h->replay.assign(channels, nullptr);
-    if (ops->make_replay) {
-        for (uint32_t c = 0; c < channels; c++) h->replay[c] = ops->make_replay();
+    if (h->sink.init(proto, channels) != DH_OK) {
+        delete h;
+        return DH_E_NOMEM;
     }
     std::vector<uint8_t> init((size_t) channels * ops->state_size);
     ops->init_states(init.data(), channels);
@@ -231,8 +167,6 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
         if (e == cudaSuccess) e = cudaMemset(h->d_counts_set[set], 0, 3 * (size_t) channels * sizeof(uint32_t));
     }
     if (e == cudaSuccess) e = cudaMalloc(&h->d_slot_filter, channels);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**) &h->h_counts, 3 * (size_t) channels * sizeof(uint32_t),
-                                            cudaHostAllocDefault);
     if (e != cudaSuccess) {
         dh::set_error("dh_decoder_create: %s", cudaGetErrorString(e));
         dh_decoder_destroy(h);
@@ -319,36 +253,36 @@ int dh_decoder_collect_results(dh_decoder* h, int set, void* stream) {
 
 int dh_decoder_output(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len) {
     DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_output: bad handle or channel");
-    if (data) *data = reinterpret_cast<const uint8_t*>(h->results[channel].bytes.data());
-    if (len) *len = h->results[channel].bytes.size();
+    if (data) *data = reinterpret_cast<const uint8_t*>(h->sink.results[channel].bytes.data());
+    if (len) *len = h->sink.results[channel].bytes.size();
     return DH_OK;
 }
 
 int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, size_t* len) {
     DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_meta: bad handle or channel");
-    if (text) *text = h->results[channel].meta.data();
-    if (len) *len = h->results[channel].meta.size();
+    if (text) *text = h->sink.results[channel].meta.data();
+    if (len) *len = h->sink.results[channel].meta.size();
     return DH_OK;
 }
 
 int dh_decoder_meta_kv(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len) {
     DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_decoder_meta_kv: bad handle or channel");
-    if (data) *data = reinterpret_cast<const uint8_t*>(h->results[channel].meta_kv.data());
-    if (len) *len = h->results[channel].meta_kv.size();
+    if (data) *data = reinterpret_cast<const uint8_t*>(h->sink.results[channel].meta_kv.data());
+    if (len) *len = h->sink.results[channel].meta_kv.size();
     return DH_OK;
 }
 
 int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_totals: handle is NULL");
-    if (out_bytes) *out_bytes = h->total_bytes;
-    if (meta_bytes) *meta_bytes = h->total_meta;
+    if (out_bytes) *out_bytes = h->sink.total_bytes;
+    if (meta_bytes) *meta_bytes = h->sink.total_meta;
     return DH_OK;
 }
 
 int dh_decoder_stats(dh_decoder* h, uint64_t* events, uint64_t* d2h_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_stats: handle is NULL");
-    if (events) *events = h->total_events;
-    if (d2h_bytes) *d2h_bytes = h->total_d2h;
+    if (events) *events = h->sink.total_events;
+    if (d2h_bytes) *d2h_bytes = h->sink.total_d2h;
     return DH_OK;
 }
 
@@ -363,11 +297,7 @@ int dh_decoder_discard(dh_decoder* h, void* stream) {
 
 int dh_decoder_clear(dh_decoder* h) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_clear: handle is NULL");
-    for (auto& r : h->results) {
-        r.bytes.clear();
-        r.meta.clear();
-        r.meta_kv.clear();
-    }
+    h->sink.clear();
     return DH_OK;
 }
 
@@ -390,6 +320,8 @@ int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, 
     return DH_OK;
 }
 
+uint32_t dh_decoder_channels(const dh_decoder* h) { return h ? h->channels : 0; }
+
 void dh_decoder_destroy(dh_decoder* h) {
     if (!h) return;
     dh::DeviceGuard guard(h->device);
@@ -401,10 +333,7 @@ void dh_decoder_destroy(dh_decoder* h) {
         cudaFree(h->d_counts_set[set]);
     }
     cudaFree(h->d_slot_filter);
-    if (h->h_counts) cudaFreeHost(h->h_counts);
-    if (h->h_out) cudaFreeHost(h->h_out);
-    if (h->h_ev) cudaFreeHost(h->h_ev);
-    for (auto* r : h->replay) delete r;
+    h->sink.release();
     delete h;
 }
 

@@ -108,4 +108,30 @@ struct ChannelResult {
     std::string meta_kv;   // same updates as key/value records (see MetaReplay::kv_sink)
 };
 
+class MetaReplay;
+
+// Where device result blocks end up on the host: per-channel byte streams + the metadata lines replayed from the
+// 16-byte event records.  One sink serves a decoder bank (its own channels) or the gathering rank of a sharded
+// pipe (the channels of every rank, shard.cu).
+struct ResultSink {
+    uint32_t channels = 0;
+    std::vector<ChannelResult> results;
+    std::vector<MetaReplay*> replay;      // null entries: protocol without metadata plane
+    uint32_t* h_counts = nullptr;         // pinned, [3][channels]
+    uint8_t* h_out = nullptr;             // pinned staging, grown on demand
+    size_t h_out_bytes = 0;
+    DecEvent* h_ev = nullptr;
+    size_t h_ev_bytes = 0;
+    uint64_t total_bytes = 0, total_meta = 0, total_events = 0, total_d2h = 0;
+
+    int init(int proto, uint32_t nchannels);
+    // Reads one device result block — counts [3][n] (out_len, ev_len, flags), byte rows [n][out_pitch], event rows
+    // [n][ev_pitch records] — of the sink channels [c0, c0 + n): copies the used widths to pinned memory on `st`
+    // (synchronises it), appends the bytes and replays the events in order.  The flag words are OR-ed into *flags.
+    int ingest(const uint32_t* d_counts, const uint8_t* d_out, size_t out_pitch, const DecEvent* d_ev, size_t ev_pitch,
+               uint32_t n, uint32_t c0, cudaStream_t st, uint32_t* flags);
+    void clear();
+    void release();
+};
+
 }  // namespace dh

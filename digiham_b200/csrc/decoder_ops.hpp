@@ -18,10 +18,24 @@ struct ProtoOps {
     MetaReplay* (*make_replay)();      // may be null: protocol without metadata plane
 };
 
+const ProtoOps* proto_ops(int proto);   // null for an unknown protocol id
 const ProtoOps* dmr_ops();
 const ProtoOps* pocsag_ops();
 const ProtoOps* ysf_ops();
 const ProtoOps* nxdn_ops();
 const ProtoOps* dstar_ops();
+
+// Device view of one of the two result sets of a decoder bank (for stages that consume the results on the device,
+// e.g. the wire packing of a sharded pipe): fixed-slot rows + per-channel counts [3][channels] (out_len, ev_len, flags).
+struct DecoderView {
+    uint8_t* out;
+    uint32_t out_cap;
+    DecEvent* ev;
+    uint32_t ev_cap;
+    uint32_t* counts;
+    uint32_t channels;
+    size_t max_syms;   // per-call symbol capacity the slots were sized for
+};
+int decoder_view(dh_decoder* h, int set, DecoderView* view);
 
 }  // namespace dh

@@ -492,6 +492,7 @@ struct dh_demod {
     int cur = 0;
     size_t pitch = 0;      // elements per work row
     size_t max_n = 0;      // chunk capacity of the work rows
+    bool smem_attr_set = false;   // the kernel variant and its dynamic smem size are fixed per bank
 };
 
 namespace {
@@ -650,7 +651,9 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
 #define DH_LAUNCH_DEMOD(GG, SS, TT)                                                                                  \
     do {                                                                                                             \
-        DH_CUDA(cudaFuncSetAttribute(demod_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem)); \
+        if (!h->smem_attr_set)                                                                                       \
+            DH_CUDA(cudaFuncSetAttribute(demod_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                         (int) smem));                                                               \
         demod_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                          \
     } while (0)
     if (G == 10 && h->sps == 10) {
@@ -671,6 +674,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     }
 #undef DH_LAUNCH_DEMOD
     DH_CUDA(cudaGetLastError());
+    h->smem_attr_set = true;
     h->cur ^= 1;   // the carried tails now sit in the other buffer
     return DH_OK;
 }
@@ -681,6 +685,8 @@ int dh_demod_reset(dh_demod* h, void* stream) {
     DH_CUDA(cudaMemsetAsync(h->d_state, 0, (size_t) h->channels * sizeof(ChannelState), (cudaStream_t) stream));
     return DH_OK;
 }
+
+uint32_t dh_demod_channels(const dh_demod* h) { return h ? h->channels : 0; }
 
 void dh_demod_destroy(dh_demod* h) {
     if (!h) return;

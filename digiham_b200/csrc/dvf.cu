@@ -187,6 +187,8 @@ int dh_dvf_reset(dh_dvf* h, void* stream) {
     return DH_OK;
 }
 
+uint32_t dh_dvf_channels(const dh_dvf* h) { return h ? h->channels : 0; }
+
 void dh_dvf_destroy(dh_dvf* h) {
     if (!h) return;
     dh::DeviceGuard guard(h->device);

@@ -56,6 +56,8 @@ void dh_host_scratch_release(const void* handle) {
 int dh_rrc_process_host(dh_rrc* h, uint32_t channels, const float* h_in, size_t in_pitch, float* h_out,
                         size_t out_pitch, size_t n) {
     DH_REQUIRE(h != nullptr && h_in != nullptr && h_out != nullptr, DH_E_INVALID, "dh_rrc_process_host: NULL argument");
+    DH_REQUIRE(channels == dh_rrc_channels(h), DH_E_INVALID, "dh_rrc_process_host: channels=%u but the bank has %u",
+               channels, dh_rrc_channels(h));
     if (n == 0) return DH_OK;
     DH_REQUIRE(in_pitch >= n && out_pitch >= n, DH_E_INVALID, "dh_rrc_process_host: pitch < n");
     Scratch& s = scratch_of(h);
@@ -76,6 +78,8 @@ int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_in, siz
                           uint8_t* h_sym, size_t sym_pitch, uint32_t* h_nsym) {
     DH_REQUIRE(h != nullptr && h_sym != nullptr && h_nsym != nullptr, DH_E_INVALID,
                "dh_demod_process_host: NULL argument");
+    DH_REQUIRE(channels == dh_demod_channels(h), DH_E_INVALID, "dh_demod_process_host: channels=%u but the bank has %u",
+               channels, dh_demod_channels(h));
     if (n == 0) {
         for (uint32_t c = 0; c < channels; c++) h_nsym[c] = 0;
         return DH_OK;
@@ -106,6 +110,8 @@ int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_in, siz
 int dh_decoder_process_host(dh_decoder* h, uint32_t channels, const uint8_t* h_sym, size_t sym_pitch,
                             const uint32_t* h_nsym) {
     DH_REQUIRE(h != nullptr && h_nsym != nullptr, DH_E_INVALID, "dh_decoder_process_host: NULL argument");
+    DH_REQUIRE(channels == dh_decoder_channels(h), DH_E_INVALID,
+               "dh_decoder_process_host: channels=%u but the bank has %u", channels, dh_decoder_channels(h));
     uint32_t mx = 0;
     for (uint32_t c = 0; c < channels; c++) mx = h_nsym[c] > mx ? h_nsym[c] : mx;
     if (mx == 0) return DH_OK;
@@ -127,6 +133,8 @@ int dh_decoder_process_host(dh_decoder* h, uint32_t channels, const uint8_t* h_s
 int dh_dvf_process_host(dh_dvf* h, uint32_t channels, const int16_t* h_in, size_t in_pitch, int16_t* h_out,
                         size_t out_pitch, size_t n) {
     DH_REQUIRE(h != nullptr && h_in != nullptr && h_out != nullptr, DH_E_INVALID, "dh_dvf_process_host: NULL argument");
+    DH_REQUIRE(channels == dh_dvf_channels(h), DH_E_INVALID, "dh_dvf_process_host: channels=%u but the bank has %u",
+               channels, dh_dvf_channels(h));
     if (n == 0) return DH_OK;
     DH_REQUIRE(in_pitch >= n && out_pitch >= n, DH_E_INVALID, "dh_dvf_process_host: pitch < n");
     Scratch& s = scratch_of(h);

@@ -42,7 +42,9 @@ struct dh_pipe {
     uint64_t submitted = 0, collected = 0;
     // optional per-stage device timing: CUDA events around every kernel, on the stream it is launched on
     bool profiling = false;
-    std::vector<cudaEvent_t> events;   // groups of 6: K1 start/end, K2 start/end, decoder start/end
+    std::vector<cudaEvent_t> events;   // pool; groups of 6: K1 start/end, K2 start/end, decoder start/end
+    size_t events_used = 0;            // recorded since the last dh_pipe_stage_times
+    cudaStream_t last_k1_stream = nullptr;   // stream the first kernel of the most recent call was enqueued on
     uint64_t launches = 0;             // kernels launched by this pipe since creation
     // Software pipelining inside one process call: the chunk is cut into sub-chunks; K1 of sub-chunk c+1 (stream
     // a) overlaps K2 + decoder of sub-chunk c (stream b, higher priority).  K1 is issue-bound, K2 and the decoder
@@ -121,24 +123,32 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
 
 namespace {
 
+constexpr size_t kMaxTimedCalls = 65536;
+
 // one sub-chunk through the three stages; k1/k23 are the streams of K1 and of K2 + decoder
-int run_stages(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, cudaStream_t k1, cudaStream_t k23,
-               cudaEvent_t k1_done, cudaEvent_t k2_done) {
+int run_stages(dh_pipe* h, const void* d_in, size_t in_pitch, size_t n, cudaStream_t k1, cudaStream_t k23,
+               cudaEvent_t k1_done, cudaEvent_t k2_done, bool s16 = false) {
+    // per-stage timing events come from a pool that is recycled by dh_pipe_stage_times; a profiled pipe that is
+    // never queried stops recording once kMaxTimedCalls calls are pending instead of growing without bound
     auto mark = [&](cudaStream_t st) -> int {
-        if (!h->profiling) return DH_OK;
-        cudaEvent_t e;
-        DH_CUDA(cudaEventCreate(&e));
-        DH_CUDA(cudaEventRecord(e, st));
-        h->events.push_back(e);
+        if (!h->profiling || h->events_used >= kMaxTimedCalls * 6) return DH_OK;
+        if (h->events_used == h->events.size()) {
+            cudaEvent_t e;
+            DH_CUDA(cudaEventCreate(&e));
+            h->events.push_back(e);
+        }
+        DH_CUDA(cudaEventRecord(h->events[h->events_used++], st));
         return DH_OK;
     };
+    h->last_k1_stream = k1;
     int rc;
     if (h->rrc) {
         // the demodulator's input rows alternate between two buffers from call to call
         rc = dh_demod_reserve(h->demod, h->max_chunk, &h->d_filt, &h->filt_pitch);
         if (rc != DH_OK) return rc;
         if ((rc = mark(k1)) != DH_OK) return rc;
-        rc = dh_rrc_process(h->rrc, d_in, in_pitch, h->d_filt, h->filt_pitch, n, k1);
+        rc = s16 ? dh_rrc_process_s16(h->rrc, static_cast<const int16_t*>(d_in), in_pitch, h->d_filt, h->filt_pitch, n, k1)
+                 : dh_rrc_process(h->rrc, static_cast<const float*>(d_in), in_pitch, h->d_filt, h->filt_pitch, n, k1);
         if (rc != DH_OK) return rc;
         h->launches++;
         if ((rc = mark(k1)) != DH_OK) return rc;
@@ -152,7 +162,8 @@ int run_stages(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, cudaStr
         if ((rc = mark(k1)) != DH_OK) return rc;
         if ((rc = mark(k1)) != DH_OK) return rc;
         if ((rc = mark(k23)) != DH_OK) return rc;
-        rc = dh_demod_process(h->demod, d_in, in_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym, k23);
+        rc = dh_demod_process(h->demod, static_cast<const float*>(d_in), in_pitch, n, h->d_sym, h->sym_pitch, h->d_nsym,
+                              k23);
     }
     if (rc != DH_OK) return rc;
     h->launches++;
@@ -167,12 +178,21 @@ int run_stages(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, cudaStr
 
 }  // namespace
 
-int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream) {
+}  // extern "C"
+
+namespace {
+
+int pipe_process_device(dh_pipe* h, const void* d_in_v, size_t in_pitch, size_t n, void* stream, bool s16) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_device: handle is NULL");
     DH_REQUIRE(n <= h->max_chunk, DH_E_INVALID, "dh_pipe_process_device: n=%zu exceeds max_chunk=%zu", n, h->max_chunk);
+    DH_REQUIRE(!s16 || h->rrc, DH_E_UNSUPPORTED,
+               "dh_pipe_process_device_s16: this pipe has no RRC stage to fuse the int16 conversion into");
     if (n == 0) return DH_OK;
     cudaStream_t user = (cudaStream_t) stream;
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "dh_pipe_process_device: cannot switch to device %d", h->device);
+    const char* d_in = static_cast<const char*>(d_in_v);
+    const size_t elem = s16 ? sizeof(int16_t) : sizeof(float);
     if (h->async_mode && h->rrc) {
         // K1(i) may start as soon as the input is ready and K2(i - 2), the previous reader of the demodulator rows
         // it alternates into, is done; K2(i) + decoder(i) follow on stream b
@@ -184,14 +204,15 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
         DH_CUDA(cudaEventRecord(h->ev_start, user));
         DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_start, 0));
         if (i >= 2) DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_a2[(i - 2) & 3], 0));
-        int rc = run_stages(h, d_in, in_pitch, n, h->sa, h->sb, h->ev_a1[i & 3], h->ev_a2[i & 3]);
+        int rc = run_stages(h, d_in, in_pitch, n, h->sa, h->sb, h->ev_a1[i & 3], h->ev_a2[i & 3], s16);
         if (rc != DH_OK) return rc;
         DH_CUDA(cudaEventRecord(h->ev_done, h->sb));
         h->async_pending = true;
         h->ev_last_k1 = h->ev_a1[i & 3];
         return DH_OK;
     }
-    if (!h->rrc || h->sub_chunk == 0 || n <= h->sub_chunk) return run_stages(h, d_in, in_pitch, n, user, user, nullptr, nullptr);
+    if (!h->rrc || h->sub_chunk == 0 || n <= h->sub_chunk)
+        return run_stages(h, d_in, in_pitch, n, user, user, nullptr, nullptr, s16);
 
     // pipelined: K1(c) on stream a; K2(c) + decoder(c) on stream b after K1(c); K1(c) may only overwrite the
     // demodulator rows it alternates into once K2(c - 2), their previous reader, is done
@@ -211,7 +232,7 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
         const size_t off = c * sub;
         const size_t len = n - off < sub ? n - off : sub;
         if (c >= 2) DH_CUDA(cudaStreamWaitEvent(h->sa, h->ev_k2[c - 2], 0));
-        int rc = run_stages(h, d_in + off, in_pitch, len, h->sa, h->sb, h->ev_k1[c], h->ev_k2[c]);
+        int rc = run_stages(h, d_in + off * elem, in_pitch, len, h->sa, h->sb, h->ev_k1[c], h->ev_k2[c], s16);
         if (rc != DH_OK) return rc;
     }
     // everything on stream a precedes the last K2 on stream b
@@ -220,9 +241,30 @@ int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_
     return DH_OK;
 }
 
+}  // namespace
+
+extern "C" {
+
+int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream) {
+    return pipe_process_device(h, d_in, in_pitch, n, stream, false);
+}
+
+int dh_pipe_process_device_s16(dh_pipe* h, const int16_t* d_in, size_t in_pitch, size_t n, void* stream) {
+    return pipe_process_device(h, d_in, in_pitch, n, stream, true);
+}
+
+int dh_pipe_input_event(dh_pipe* h, void* event) {
+    DH_REQUIRE(h != nullptr && event != nullptr, DH_E_INVALID, "dh_pipe_input_event: NULL argument");
+    dh::DeviceGuard guard(h->device);
+    // the first kernel of a call is the only reader of the caller's block (K1, or K2 for the pipes without an RRC
+    // stage); nothing else has been enqueued on its stream since
+    DH_CUDA(cudaEventRecord((cudaEvent_t) event, h->last_k1_stream));
+    return DH_OK;
+}
+
 int dh_pipe_set_sub_chunk(dh_pipe* h, size_t sub_chunk) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_set_sub_chunk: handle is NULL");
-    DH_REQUIRE(sub_chunk % 4 == 0, DH_E_INVALID, "dh_pipe_set_sub_chunk: must be a multiple of 4");
+    DH_REQUIRE(sub_chunk % 8 == 0, DH_E_INVALID, "dh_pipe_set_sub_chunk: must be a multiple of 8");
     h->sub_chunk = sub_chunk;
     return DH_OK;
 }
@@ -264,7 +306,7 @@ int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_stage_times: handle is NULL");
     dh::DeviceGuard guard(h->device);
     double acc[3] = {0, 0, 0};
-    const size_t ncalls = h->events.size() / 6;
+    const size_t ncalls = h->events_used / 6;
     for (size_t c = 0; c < ncalls; c++) {
         for (int k = 0; k < 3; k++) {
             float t = 0;
@@ -273,8 +315,7 @@ int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
             acc[k] += t;
         }
     }
-    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
-    h->events.clear();
+    h->events_used = 0;   // the events go back to the pool
     if (ms) for (int k = 0; k < 3; k++) ms[k] = acc[k];
     if (calls) *calls = ncalls;
     return DH_OK;
@@ -282,12 +323,36 @@ int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
 
 uint64_t dh_pipe_launch_count(const dh_pipe* h) { return h ? h->launches : 0; }
 
-int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// host row pitch (elements) that allows one contiguous transfer: float32 rows are 16-byte multiples at n % 4 == 0,
+// int16 rows at n % 8 == 0
+size_t host_pitch_of(const dh_pipe* h, bool s16) {
+    return s16 ? (h->max_chunk + 7) & ~(size_t) 7 : (h->max_chunk + 3) & ~(size_t) 3;
+}
+
+int upload(const dh_pipe* h, void* d_dst, const void* h_in, size_t in_pitch, size_t n, bool s16, cudaStream_t st) {
+    const size_t elem = s16 ? sizeof(int16_t) : sizeof(float);
+    const size_t pitch = host_pitch_of(h, s16);
+    if (in_pitch == pitch) {
+        // one contiguous transfer
+        DH_CUDA(cudaMemcpyAsync(d_dst, h_in, (size_t) h->channels * in_pitch * elem, cudaMemcpyHostToDevice, st));
+    } else {
+        DH_CUDA(cudaMemcpy2DAsync(d_dst, pitch * elem, h_in, in_pitch * elem, n * elem, h->channels,
+                                  cudaMemcpyHostToDevice, st));
+    }
+    return DH_OK;
+}
+
+int pipe_process_host(dh_pipe* h, const void* h_in, size_t in_pitch, size_t n, void* stream, bool s16) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_process_host: handle is NULL");
     DH_REQUIRE(n <= h->max_chunk, DH_E_INVALID, "dh_pipe_process_host: n=%zu exceeds max_chunk=%zu", n, h->max_chunk);
     if (n == 0) return DH_OK;
     DH_REQUIRE(h_in != nullptr && in_pitch >= n, DH_E_INVALID, "dh_pipe_process_host: bad input buffer");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "dh_pipe_process_host: cannot switch to device %d", h->device);
     if (!h->d_stage) {
         h->stage_pitch = (h->max_chunk + 3) & ~(size_t) 3;
         DH_CUDA(cudaMalloc(&h->d_stage, (size_t) h->channels * h->stage_pitch * sizeof(float)));
@@ -296,25 +361,22 @@ int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t 
     cudaStream_t st = (cudaStream_t) stream;
     // asynchronous mode: the staging block is still being read by K1 of the previous call (internal stream)
     if (h->async_pending && h->ev_last_k1) DH_CUDA(cudaStreamWaitEvent(st, h->ev_last_k1, 0));
-    if (in_pitch == h->stage_pitch) {
-        // one contiguous transfer
-        DH_CUDA(cudaMemcpyAsync(h->d_stage, h_in, (size_t) h->channels * in_pitch * sizeof(float),
-                                cudaMemcpyHostToDevice, st));
-    } else {
-        DH_CUDA(cudaMemcpy2DAsync(h->d_stage, h->stage_pitch * sizeof(float), h_in, in_pitch * sizeof(float),
-                                  n * sizeof(float), h->channels, cudaMemcpyHostToDevice, st));
-    }
-    return dh_pipe_process_device(h, h->d_stage, h->stage_pitch, n, stream);
+    int rc = upload(h, h->d_stage, h_in, in_pitch, n, s16, st);
+    if (rc != DH_OK) return rc;
+    return pipe_process_device(h, h->d_stage, host_pitch_of(h, s16), n, stream, s16);
 }
 
-int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n) {
+int pipe_submit_host(dh_pipe* h, const void* h_in, size_t in_pitch, size_t n, bool s16) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_submit_host: handle is NULL");
     DH_REQUIRE(n > 0 && n <= h->max_chunk, DH_E_INVALID, "dh_pipe_submit_host: n=%zu out of range (max_chunk=%zu)", n,
                h->max_chunk);
     DH_REQUIRE(h_in != nullptr && in_pitch >= n, DH_E_INVALID, "dh_pipe_submit_host: bad input buffer");
+    DH_REQUIRE(!s16 || h->rrc, DH_E_UNSUPPORTED,
+               "dh_pipe_submit_host_s16: this pipe has no RRC stage to fuse the int16 conversion into");
     DH_REQUIRE(h->submitted - h->collected < 2, DH_E_STATE,
                "dh_pipe_submit_host: two steps are already in flight, call dh_pipe_collect_step first");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "dh_pipe_submit_host: cannot switch to device %d", h->device);
     const int slot = (int) (h->submitted & 1);
     if (!h->s_copy) {
         h->stage_pitch = (h->max_chunk + 3) & ~(size_t) 3;
@@ -331,28 +393,40 @@ int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n
     }
     // upload into the slot once K1 of the step that used it two submissions ago has read it
     if (h->submitted >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_consumed[slot], 0));
-    if (in_pitch == h->stage_pitch) {
-        DH_CUDA(cudaMemcpyAsync(h->d_slot[slot], h_in, (size_t) h->channels * in_pitch * sizeof(float),
-                                cudaMemcpyHostToDevice, h->s_copy));
-    } else {
-        DH_CUDA(cudaMemcpy2DAsync(h->d_slot[slot], h->stage_pitch * sizeof(float), h_in, in_pitch * sizeof(float),
-                                  n * sizeof(float), h->channels, cudaMemcpyHostToDevice, h->s_copy));
-    }
+    int rc = upload(h, h->d_slot[slot], h_in, in_pitch, n, s16, h->s_copy);
+    if (rc != DH_OK) return rc;
     DH_CUDA(cudaEventRecord(h->ev_uploaded[slot], h->s_copy));
     DH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_uploaded[slot], 0));
     // results of this step go to the result set of its parity
-    int rc = dh_decoder_select_results(h->decoder, slot);
+    rc = dh_decoder_select_results(h->decoder, slot);
     if (rc != DH_OK) return rc;
-    const size_t saved_sub = h->sub_chunk;
-    h->sub_chunk = 0;
-    rc = run_stages(h, h->d_slot[slot], h->stage_pitch, n, h->s_compute, h->s_compute, nullptr, nullptr);
-    h->sub_chunk = saved_sub;
+    rc = run_stages(h, h->d_slot[slot], host_pitch_of(h, s16), n, h->s_compute, h->s_compute, nullptr, nullptr, s16);
     if (rc != DH_OK) return rc;
     // K1 is the only reader of the slot, but the stages are serialised on one stream anyway
     DH_CUDA(cudaEventRecord(h->ev_consumed[slot], h->s_compute));
     DH_CUDA(cudaEventRecord(h->ev_decoded[slot], h->s_compute));
     h->submitted++;
     return DH_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream) {
+    return pipe_process_host(h, h_in, in_pitch, n, stream, false);
+}
+
+int dh_pipe_process_host_s16(dh_pipe* h, const int16_t* h_in, size_t in_pitch, size_t n, void* stream) {
+    return pipe_process_host(h, h_in, in_pitch, n, stream, true);
+}
+
+int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n) {
+    return pipe_submit_host(h, h_in, in_pitch, n, false);
+}
+
+int dh_pipe_submit_host_s16(dh_pipe* h, const int16_t* h_in, size_t in_pitch, size_t n) {
+    return pipe_submit_host(h, h_in, in_pitch, n, true);
 }
 
 int dh_pipe_collect_step(dh_pipe* h) {
@@ -399,7 +473,11 @@ int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t ca
     return DH_OK;
 }
 
-size_t dh_pipe_host_pitch(const dh_pipe* h) { return h ? (h->max_chunk + 3) & ~(size_t) 3 : 0; }
+size_t dh_pipe_host_pitch(const dh_pipe* h) { return h ? host_pitch_of(h, false) : 0; }
+
+size_t dh_pipe_host_pitch_s16(const dh_pipe* h) { return h ? host_pitch_of(h, true) : 0; }
+
+uint32_t dh_pipe_channels(const dh_pipe* h) { return h ? h->channels : 0; }
 
 void dh_pipe_destroy(dh_pipe* h) {
     if (!h) return;

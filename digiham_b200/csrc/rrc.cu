@@ -45,7 +45,7 @@ struct alignas(16) TapBlock {
 __host__ __device__ constexpr int pad4(int r) { return (r + 3) & ~3; }
 
 struct RrcParams {
-    const float* in;
+    const void* in;         // float32 rows, or int16 rows (S16 kernels: dh_rrc_process_s16)
     float* out;
     const float* hist_in;   // [channels][nz]  last nz inputs before this call
     float* hist_out;        // [channels][nz]  last nz inputs after this call
@@ -61,7 +61,8 @@ struct RrcParams {
 
 // Outputs per thread for a call of n samples.  A CTA slot costs the same whether its tile is full or ragged (the
 // surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..19 to
-// minimise tiles * (work per tile): e.g. n = 48000 -> R = 15, 25 full tiles instead of 22 + a ragged one at R = 17.
+// minimise tiles * (work per tile): e.g. n = 48000 -> R = 19, 20 tiles instead of 22 + a ragged one at R = 17
+// (R = 15, 25 equal tiles, when the smaller register footprint is preferred: dh_rrc_set_tile_preference).
 inline int pick_r(size_t n, int nz, bool prefer_small) {
     static const int forced = [] {   // tuning switch, read once
         const char* env = getenv("DH_RRC_R");
@@ -86,8 +87,19 @@ inline int pick_r(size_t n, int nz, bool prefer_small) {
     return best;
 }
 
-// NZ_CT > 0: compile-time tap count; RECIP: scale by the reciprocal gain (built-in filters) instead of dividing
-template <int NZ_CT, bool RECIP, int kR>
+// `csdr convert -i s16 -o float` (the step in front of rrc_filter in reference examples/dmr-decoder.sh:13-15):
+// out = (float) in / SHRT_MAX, one IEEE float32 division.  Computed as q = f * r, q' = fma(fma(-q, 32767, f), r, q)
+// with r = fl32(1 / 32767): proven equal to the division for all 65536 inputs (tests/test_host_logic.py).
+__device__ __forceinline__ float s16_to_float(int v) {
+    const float f = (float) v;
+    const float r = 1.0f / 32767.0f;
+    const float q = __fmul_rn(f, r);
+    return __fmaf_rn(__fmaf_rn(-q, 32767.0f, f), r, q);
+}
+
+// NZ_CT > 0: compile-time tap count; RECIP: scale by the reciprocal gain (built-in filters) instead of dividing;
+// S16: the input rows are int16 and are converted while the tile sits in shared memory (fused csdr convert)
+template <int NZ_CT, bool RECIP, int kR, bool S16>
 __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant__ RrcParams p,
                                                           const __grid_constant__ TapBlock taps) {
     constexpr int kTile = kThreads * kR;
@@ -99,9 +111,14 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
     const int ch = blockIdx.y;
     const int t0 = tile * kTile;
     const int valid = min(kTile, p.n - t0);
-    const float* in_row = p.in + (size_t) ch * p.in_pitch;
+    const float* in_row = static_cast<const float*>(p.in) + (size_t) ch * p.in_pitch;
+    const int16_t* in_row16 = static_cast<const int16_t*>(p.in) + (size_t) ch * p.in_pitch;
     float* out_row = p.out + (size_t) ch * p.out_pitch;
     const int tid = threadIdx.x;
+    // S16: the raw int16 tile lands in the upper half of the float buffer (bytes [2F, 4F), F = nz + kTile) and is
+    // converted into place through registers; the FIR history stays float32 (tile 0 gets its halo as floats)
+    const int F = nz + kTile;
+    int16_t* raw = reinterpret_cast<int16_t*>(s) + F;
 
     if (tid == 0) {
         dh::mbar_init(&bar, 1);
@@ -109,12 +126,21 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
     }
     __syncthreads();
     if (tid == 0) {
-        const uint32_t main_bytes = (uint32_t) ((valid + 3) & ~3) * 4u;
-        const uint32_t halo_bytes = (uint32_t) nz * 4u;
-        dh::mbar_expect_tx(&bar, main_bytes + halo_bytes);
-        const float* halo = tile == 0 ? p.hist_in + (size_t) ch * nz : in_row + t0 - nz;
-        dh::bulk_g2s(s, halo, halo_bytes, &bar);
-        dh::bulk_g2s(s + nz, in_row + t0, main_bytes, &bar);
+        if (S16) {
+            const uint32_t main_bytes = (uint32_t) ((valid + 7) & ~7) * 2u;
+            const uint32_t halo_bytes = tile == 0 ? (uint32_t) nz * 4u : (uint32_t) nz * 2u;
+            dh::mbar_expect_tx(&bar, main_bytes + halo_bytes);
+            if (tile == 0) dh::bulk_g2s(s, p.hist_in + (size_t) ch * nz, halo_bytes, &bar);
+            else dh::bulk_g2s(raw, in_row16 + t0 - nz, halo_bytes, &bar);
+            dh::bulk_g2s(raw + nz, in_row16 + t0, main_bytes, &bar);
+        } else {
+            const uint32_t main_bytes = (uint32_t) ((valid + 3) & ~3) * 4u;
+            const uint32_t halo_bytes = (uint32_t) nz * 4u;
+            dh::mbar_expect_tx(&bar, main_bytes + halo_bytes);
+            const float* halo = tile == 0 ? p.hist_in + (size_t) ch * nz : in_row + t0 - nz;
+            dh::bulk_g2s(s, halo, halo_bytes, &bar);
+            dh::bulk_g2s(s + nz, in_row + t0, main_bytes, &bar);
+        }
     }
 
     // carry the FIR history across calls: the CTA of the last tile publishes the last nz inputs of the stream
@@ -123,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
         float* hout = p.hist_out + (size_t) ch * nz;
         for (int j = tid; j < nz; j += kThreads) {
             int idx = p.n - nz + j;
-            hout[j] = idx >= 0 ? in_row[idx] : hin[nz + idx];
+            hout[j] = idx >= 0 ? (S16 ? s16_to_float(in_row16[idx]) : in_row[idx]) : hin[nz + idx];
         }
     }
 
@@ -136,6 +162,35 @@ __global__ void __launch_bounds__(kThreads) rrc_fir_kernel(const __grid_constant
     }
 
     dh::mbar_wait(&bar, 0);
+
+    if (S16) {
+        // pairs of samples: one 32-bit shared load, two conversions, one 64-bit store; a float pair only overwrites
+        // raw samples of lower or equal index, and every thread holds its raw words in registers before anybody writes
+        constexpr int kMaxPairs = (kMaxZeros + kTile) / 2;
+        constexpr int kIter = (kMaxPairs + kThreads - 1) / kThreads;
+        const uint32_t* raw32 = reinterpret_cast<const uint32_t*>(raw);
+        const int first = tile == 0 ? nz / 2 : 0;                      // tile 0: the halo already is float32
+        const int last = (nz + ((valid + 7) & ~7)) / 2;                 // pairs [first, last)
+        constexpr int kIterCt = NZ_CT > 0 ? ((NZ_CT + kTile) / 2 + kThreads - 1) / kThreads : kIter;
+        uint32_t held[kIterCt];
+#pragma unroll
+        for (int m = 0; m < kIterCt; m++) {
+            const int i = first + tid + m * kThreads;
+            held[m] = i < last ? raw32[i] : 0u;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int m = 0; m < kIterCt; m++) {
+            const int i = first + tid + m * kThreads;
+            if (i < last) {
+                float2 v;
+                v.x = s16_to_float((int) (short) (held[m] & 0xffffu));
+                v.y = s16_to_float((int) (short) (held[m] >> 16));
+                reinterpret_cast<float2*>(s)[i] = v;
+            }
+        }
+        __syncthreads();
+    }
 
     // s[j] = x[t0 - nz + j]; output r of this thread is sample t0 + base + r and needs s[base + r + i], i = 0..nz
     const int base = tid * kR;
@@ -292,25 +347,33 @@ int dh_rrc_create_custom(dh_rrc** out, int device, uint32_t channels, uint32_t n
     return rrc_build(out, device, channels, n_zeros, gain, 0, h_coeffs);
 }
 
-int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
-                   void* stream) {
-    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_process: handle is NULL");
+}  // extern "C"
+
+namespace {
+
+int rrc_launch(dh_rrc* h, const void* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n, void* stream,
+               bool s16, const char* who) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "%s: handle is NULL", who);
     if (n == 0) return DH_OK;
-    DH_REQUIRE(d_in != nullptr && d_out != nullptr, DH_E_INVALID, "dh_rrc_process: NULL buffer");
-    DH_REQUIRE(d_in != d_out, DH_E_INVALID, "dh_rrc_process: in-place operation is not supported");
+    DH_REQUIRE(d_in != nullptr && d_out != nullptr, DH_E_INVALID, "%s: NULL buffer", who);
+    DH_REQUIRE(d_in != (const void*) d_out, DH_E_INVALID, "%s: in-place operation is not supported", who);
     DH_REQUIRE(((uintptr_t) d_in % 16 == 0) && ((uintptr_t) d_out % 16 == 0), DH_E_INVALID,
-               "dh_rrc_process: buffers must be 16-byte aligned");
+               "%s: buffers must be 16-byte aligned", who);
     const size_t n4 = (n + 3) & ~(size_t) 3;
-    DH_REQUIRE(in_pitch % 4 == 0 && out_pitch % 4 == 0 && in_pitch >= n4 && out_pitch >= n4, DH_E_INVALID,
-               "dh_rrc_process: pitches must be multiples of 4 and >= n rounded up to 4 (n=%zu in=%zu out=%zu)", n,
-               in_pitch, out_pitch);
-    DH_REQUIRE(n <= 0x7fffffffu - kMaxTile, DH_E_INVALID, "dh_rrc_process: n too large");
+    const size_t in_unit = s16 ? 8 : 4;   // 16-byte rows
+    const size_t n_in = (n + in_unit - 1) / in_unit * in_unit;
+    DH_REQUIRE(in_pitch % in_unit == 0 && out_pitch % 4 == 0 && in_pitch >= n_in && out_pitch >= n4, DH_E_INVALID,
+               "%s: pitches must be multiples of %zu (in) / 4 (out) and >= n rounded up (n=%zu in=%zu out=%zu)", who,
+               in_unit, n, in_pitch, out_pitch);
+    DH_REQUIRE(!s16 || h->nz % 8 == 0, DH_E_UNSUPPORTED, "%s: int16 input needs nZeros %% 8 == 0", who);
+    DH_REQUIRE(n <= 0x7fffffffu - kMaxTile, DH_E_INVALID, "%s: n too large", who);
     const int r = pick_r(n, h->nz, h->prefer_small_tiles != 0);
     const size_t tile = (size_t) kThreads * r;
     const size_t tiles = (n + tile - 1) / tile;
-    DH_REQUIRE(tiles <= 0x7fffffffu, DH_E_INVALID, "dh_rrc_process: too many tiles");
+    DH_REQUIRE(tiles <= 0x7fffffffu, DH_E_INVALID, "%s: too many tiles", who);
 
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "%s: cannot switch to device %d", who, h->device);
     RrcParams p;
     p.in = d_in;
     p.out = d_out;
@@ -335,17 +398,23 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
     size_t smem = (size_t) (h->nz + tile) * sizeof(float);
     const int which = h->nz == 80 && h->mul_recip ? 0 : (h->nz == 160 && h->mul_recip ? 1 : 2);
     if (which == 2 && h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
-#define DH_LAUNCH_RRC(RR)                                                                       \
-    do {                                                                                        \
-        if (which == 0) rrc_fir_kernel<80, true, RR><<<grid, kThreads, smem, st>>>(q, h->taps);  \
-        else if (which == 1) rrc_fir_kernel<160, true, RR><<<grid, kThreads, smem, st>>>(q, h->taps); \
-        else rrc_fir_kernel<0, false, RR><<<grid, kThreads, smem, st>>>(q, h->taps);             \
+#define DH_LAUNCH_RRC2(RR, SS)                                                                          \
+    do {                                                                                                \
+        if (which == 0) rrc_fir_kernel<80, true, RR, SS><<<grid, kThreads, smem, st>>>(q, h->taps);      \
+        else if (which == 1) rrc_fir_kernel<160, true, RR, SS><<<grid, kThreads, smem, st>>>(q, h->taps); \
+        else rrc_fir_kernel<0, false, RR, SS><<<grid, kThreads, smem, st>>>(q, h->taps);                 \
+    } while (0)
+#define DH_LAUNCH_RRC(RR)                    \
+    do {                                     \
+        if (s16) DH_LAUNCH_RRC2(RR, true);   \
+        else DH_LAUNCH_RRC2(RR, false);      \
     } while (0)
     // grid = (tiles, channels); grid.y is limited to 65535, larger banks are launched in channel slices
+    const size_t in_elem = s16 ? sizeof(int16_t) : sizeof(float);
     for (size_t c0 = 0; c0 < h->channels; c0 += 65535) {
         const size_t cnt = std::min<size_t>(65535, h->channels - c0);
         RrcParams q = p;
-        q.in += c0 * in_pitch;
+        q.in = static_cast<const char*>(p.in) + c0 * in_pitch * in_elem;
         q.out += c0 * out_pitch;
         q.hist_in += c0 * h->nz;
         q.hist_out += c0 * h->nz;
@@ -358,10 +427,27 @@ int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, 
         }
     }
 #undef DH_LAUNCH_RRC
+#undef DH_LAUNCH_RRC2
     DH_CUDA(cudaGetLastError());
     h->cur ^= 1;
     return DH_OK;
 }
+
+}  // namespace
+
+extern "C" {
+
+int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
+                   void* stream) {
+    return rrc_launch(h, d_in, in_pitch, d_out, out_pitch, n, stream, false, "dh_rrc_process");
+}
+
+int dh_rrc_process_s16(dh_rrc* h, const int16_t* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
+                       void* stream) {
+    return rrc_launch(h, d_in, in_pitch, d_out, out_pitch, n, stream, true, "dh_rrc_process_s16");
+}
+
+uint32_t dh_rrc_channels(const dh_rrc* h) { return h ? h->channels : 0; }
 
 int dh_rrc_set_tile_preference(dh_rrc* h, int prefer_small) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_set_tile_preference: handle is NULL");

@@ -1,19 +1,33 @@
-"""Channel sharding across ranks (harness glue on top of torch.distributed).
+"""Channel sharding across ranks: ctypes glue over the dh_shard_* C ABI (include/digiham_b200.h).
 
 The path shards trivially: channels are independent, rank r of R owns the contiguous range
-[r*N/R, (r+1)*N/R) and no collective sits on the data path.  The two optional collectives move
-data in and out when a single ingest rank holds all channels: `scatter_channels` (input sample blocks, NCCL
-scatter over NVLink on GPUs, gloo on CPU) and `gather_frames` (decoded frames + metadata as fixed-slot byte rows).
+[r*N/R, (r+1)*N/R).  The data-path collectives — input scatter from the ingest rank, gather of the
+decoded frames + metadata events — live in the library (digiham_b200/csrc/shard.cu: grouped ncclSend / ncclRecv on
+device buffers, pipelined with the kernels).  torch.distributed is used for ONE thing here: handing rank 0's
+128-byte NCCL unique id to the other ranks.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
 
+from ._capi import FMT_F32, FMT_S16, SHARD_SCATTER, PROTO_DMR, Pipe, DecoderBank, check, lib, _dev_index, _stream_ptr
+
 
 def channel_range(rank, world, channels):
-    """Contiguous, balanced split: the first (channels % world) ranks get one extra channel."""
-    base, extra = divmod(channels, world)
-    start = rank * base + min(rank, extra)
-    return start, start + base + (1 if rank < extra else 0)
+    """[lo, hi) of `rank`: contiguous, balanced, the first (channels % world) ranks get one extra channel.
+    Computed by the library (dh_shard_channel_range, host-only)."""
+    lo, hi = ctypes.c_uint64(), ctypes.c_uint64()
+    check(lib().dh_shard_channel_range(int(channels), int(world), int(rank), ctypes.byref(lo), ctypes.byref(hi)))
+    return lo.value, hi.value
+
+
+def wire_layout(proto, max_chunk, channels):
+    """(bytes per channel slot, event records per channel slot, bytes of the whole wire block); host-only."""
+    a, b, c = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_size_t()
+    check(lib().dh_shard_wire_layout(int(proto), int(max_chunk), int(channels), ctypes.byref(a), ctypes.byref(b),
+                                     ctypes.byref(c)))
+    return a.value, b.value, c.value
 
 
 def _world():
@@ -22,69 +36,113 @@ def _world():
     return 0, 1
 
 
-def scatter_channels(x_full, channels, pitch, dtype=torch.float32, src=0, device="cpu"):
-    """x_full: [channels, pitch] tensor on the ingest rank (None elsewhere).  Returns this rank's rows.
-    Ranges may be ragged (channels % world != 0): rows are padded to the largest shard for the collective."""
-    rank, world = _world()
-    lo, hi = channel_range(rank, world, channels)
-    if world == 1:
-        return x_full[lo:hi]
-    rows = max(channel_range(r, world, channels)[1] - channel_range(r, world, channels)[0] for r in range(world))
-    recv = torch.empty((rows, pitch), dtype=dtype, device=device)
-    chunks = None
-    if rank == src:
-        chunks = []
-        for r in range(world):
-            a, b = channel_range(r, world, channels)
-            c = x_full[a:b]
-            if b - a < rows:
-                pad = torch.zeros((rows - (b - a), pitch), dtype=dtype, device=device)
-                c = torch.cat([c, pad], dim=0)
-            chunks.append(c.contiguous())
-    dist.scatter(recv, chunks, src=src)
-    return recv[:hi - lo]
-
-
-def pack_rows(items, width=None, device="cpu"):
-    """list of bytes objects -> (uint8 tensor [n, width], int32 lengths); vectorised (no per-row Python work)."""
-    import numpy as np
-    lens_np = np.fromiter((len(b) for b in items), dtype=np.int64, count=len(items))
-    if width is None:
-        width = int(lens_np.max()) if len(items) else 0
-    buf = np.zeros((len(items), max(1, width)), dtype=np.uint8)
-    total = int(lens_np.sum())
-    if total:
-        flat = np.frombuffer(b"".join(bytes(b) for b in items), dtype=np.uint8)
-        starts = np.cumsum(lens_np) - lens_np
-        rows = np.repeat(np.arange(len(items)), lens_np)
-        cols = np.arange(total) - np.repeat(starts, lens_np)
-        buf[rows, cols] = flat
-    return torch.from_numpy(buf).to(device), torch.from_numpy(lens_np.astype(np.int32)).to(device)
-
-
-def gather_frames(local_items, channels, dst=0, device="cpu"):
-    """local_items: list of bytes (one per local channel).  On `dst` returns the list for all channels in global
-    channel order, elsewhere None.  Uses two collectives: all_reduce(MAX) for the slot width, gather for the rows."""
+def make_comm(device):
+    """A fresh NCCL communicator over all ranks of the default process group, created by the library
+    (dh_shard_unique_id on rank 0 -> broadcast -> dh_shard_comm_init).  Returns an opaque pointer (None at world 1)."""
     rank, world = _world()
     if world == 1:
-        return list(local_items)
-    rows = max(channel_range(r, world, channels)[1] - channel_range(r, world, channels)[0] for r in range(world))
-    width = torch.tensor([max([len(b) for b in local_items] + [1])], dtype=torch.int64, device=device)
-    dist.all_reduce(width, op=dist.ReduceOp.MAX)
-    width = int(width.item())
-    padded = list(local_items) + [b""] * (rows - len(local_items))
-    buf, lens = pack_rows(padded, width, device)
-    bufs = [torch.empty_like(buf) for _ in range(world)] if rank == dst else None
-    lenss = [torch.empty_like(lens) for _ in range(world)] if rank == dst else None
-    dist.gather(buf, bufs, dst=dst)
-    dist.gather(lens, lenss, dst=dst)
-    if rank != dst:
         return None
-    out = []
-    for r in range(world):
-        a, b = channel_range(r, world, channels)
-        rb, rl = bufs[r].cpu().numpy(), lenss[r].cpu().numpy()
-        raw = rb.tobytes()
-        w = rb.shape[1]
-        out.extend(raw[i * w:i * w + int(rl[i])] for i in range(b - a))
-    return out
+    uid = (ctypes.c_uint8 * 128)()
+    if rank == 0:
+        check(lib().dh_shard_unique_id(uid))
+    box = [bytes(uid)]
+    dist.broadcast_object_list(box, src=0)
+    uid = (ctypes.c_uint8 * 128).from_buffer_copy(box[0])
+    comm = ctypes.c_void_p()
+    check(lib().dh_shard_comm_init(ctypes.byref(comm), uid, rank, world, _dev_index(device)))
+    return comm
+
+
+def destroy_comm(comm):
+    if comm:
+        check(lib().dh_shard_comm_destroy(comm))
+
+
+class ShardedPipe:
+    """One protocol pipe over all ranks (dh_shard_*): every method is collective."""
+
+    def __init__(self, channels_total, proto=PROTO_DMR, max_chunk=48000, device="cuda:0", fmt=FMT_F32, root=0,
+                 comm=None):
+        self.rank, self.world = _world()
+        self.root = root
+        self.channels_total = int(channels_total)
+        self.device = torch.device(device)
+        self.fmt = fmt
+        self._own_comm = comm is None and self.world > 1
+        self._comm = make_comm(device) if self._own_comm else comm
+        self._h = ctypes.c_void_p()
+        check(lib().dh_shard_create(ctypes.byref(self._h), self._comm, self.rank, self.world, root, _dev_index(device),
+                                    self.channels_total, proto, int(max_chunk), fmt))
+        self.lo, self.hi = channel_range(self.rank, self.world, self.channels_total)
+        # a non-owning view of this rank's pipe
+        self.pipe = Pipe.__new__(Pipe)
+        self.pipe._h = ctypes.c_void_p(lib().dh_shard_pipe(self._h))
+        self.pipe.channels = self.hi - self.lo
+        self.pipe.proto = proto
+        self.pipe.max_chunk = int(max_chunk)
+        self.pipe.device = self.device
+        self.pipe.close = lambda: None
+        self.pipe.decoder = DecoderBank.__new__(DecoderBank)
+        self.pipe.decoder._h = ctypes.c_void_p(lib().dh_pipe_decoder(self.pipe._h))
+        self.pipe.decoder.channels = self.pipe.channels
+        self.pipe.decoder.close = lambda: None
+
+    @property
+    def pitch(self):
+        return lib().dh_shard_pitch(self._h)
+
+    @property
+    def is_root(self):
+        return self.rank == self.root
+
+    def submit(self, x, n, scatter=True, stream=None):
+        """x: the device block ([channels_total, pitch] on the root when scattering, None elsewhere; this rank's
+        [local channels, pitch] otherwise), float32 or int16 according to the shard's format."""
+        ptr, pitch = (x.data_ptr(), x.stride(0)) if x is not None else (None, 0)
+        if x is not None:
+            assert x.is_cuda and x.stride(1) == 1
+            assert x.dtype == (torch.int16 if self.fmt == FMT_S16 else torch.float32)
+        check(lib().dh_shard_submit_device(self._h, ptr, pitch, int(n), SHARD_SCATTER if scatter else 0,
+                                           _stream_ptr(stream)))
+
+    def collect_step(self):
+        check(lib().dh_shard_collect_step(self._h))
+
+    def discard_step(self):
+        check(lib().dh_shard_discard_step(self._h))
+
+    def sync(self, stream=None):
+        check(lib().dh_shard_sync(self._h, _stream_ptr(stream)))
+
+    def output(self, channel):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib().dh_shard_output(self._h, int(channel), ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value) if n.value else b""
+
+    def meta(self, channel):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib().dh_shard_meta(self._h, int(channel), ctypes.byref(p), ctypes.byref(n)))
+        return ctypes.string_at(p.value, n.value) if n.value else b""
+
+    def clear(self):
+        check(lib().dh_shard_clear(self._h))
+
+    def stats(self):
+        """(kernels launched by this rank, bytes of its wire block per step, bytes read back on the root)."""
+        a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        check(lib().dh_shard_stats(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, c.value
+
+    def close(self):
+        if self._h:
+            lib().dh_shard_destroy(self._h)
+            self._h = ctypes.c_void_p()
+        if self._own_comm and self._comm:
+            destroy_comm(self._comm)
+            self._comm = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

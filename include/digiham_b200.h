@@ -49,6 +49,7 @@ extern "C" {
 #define DH_E_STATE (-3)       /* call not valid in the current state of the bank */
 #define DH_E_UNSUPPORTED (-4) /* configuration not supported by the CUDA path */
 #define DH_E_NODEVICE (-5)    /* no usable sm_100 device */
+#define DH_E_NCCL (-6)        /* an NCCL call failed (dh_shard_*) */
 
 DH_API const char* dh_last_error(void);
 /* version of this library, formatted like Digiham::version (include/version.hpp:7) */
@@ -82,7 +83,17 @@ DH_API int dh_rrc_create_custom(dh_rrc** out, int device, uint32_t channels, uin
 DH_API int dh_rrc_process(dh_rrc* h, const float* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
                    void* stream);
 /* back to power-on state (zero history) */
-/* Host-buffer variant (synchronous): h_in/h_out are [channels][pitch] in host memory; staging is internal. */
+/* The same filter fed with int16 samples: fuses `csdr convert -i s16 -o float` — the step in front of rrc_filter in
+ * the reference's pipes (examples/dmr-decoder.sh:13-15), out = (float) in / SHRT_MAX — into the tile staging of the
+ * FIR kernel, so the samples cross PCIe / NVLink / HBM as 2 bytes.  d_in rows are 16-byte aligned, in_pitch (in
+ * int16 elements) is a multiple of 8 and >= n rounded up to 8; needs nZeros % 8 == 0 (both built-in filters).
+ * float32 and int16 calls may be mixed on one bank (the carried history is float32). */
+DH_API int dh_rrc_process_s16(dh_rrc* h, const int16_t* d_in, size_t in_pitch, float* d_out, size_t out_pitch, size_t n,
+                       void* stream);
+/* number of channels of the bank */
+DH_API uint32_t dh_rrc_channels(const dh_rrc* h);
+/* Host-buffer variant (synchronous): h_in/h_out are [channels][pitch] in host memory; staging is internal.
+ * `channels` must equal the bank's channel count. */
 DH_API int dh_rrc_process_host(dh_rrc* h, uint32_t channels, const float* h_in, size_t in_pitch, float* h_out,
                                size_t out_pitch, size_t n);
 /* Tile-size policy of the FIR kernel: 0 (default) = fastest stand-alone; 1 = favour the smaller register footprint,
@@ -115,9 +126,11 @@ DH_API size_t dh_demod_max_symbols(const dh_demod* h, size_t n);
  * count for this call to d_nsym[c].  sym_pitch >= dh_demod_max_symbols(h, n). */
 DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, uint8_t* d_sym,
                             size_t sym_pitch, uint32_t* d_nsym, void* stream);
-/* Host-buffer variant (synchronous); h_nsym receives the per-channel symbol counts of this call. */
+/* Host-buffer variant (synchronous); h_nsym receives the per-channel symbol counts of this call.
+ * `channels` must equal the bank's channel count (DH_E_INVALID otherwise; likewise for the other *_process_host). */
 DH_API int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_in, size_t in_pitch, size_t n,
                                  uint8_t* h_sym, size_t sym_pitch, uint32_t* h_nsym);
+DH_API uint32_t dh_demod_channels(const dh_demod* h);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);
 
@@ -133,6 +146,7 @@ DH_API int dh_dvf_process(dh_dvf* h, const int16_t* d_in, size_t in_pitch, int16
                           size_t n, void* stream);
 DH_API int dh_dvf_process_host(dh_dvf* h, uint32_t channels, const int16_t* h_in, size_t in_pitch, int16_t* h_out,
                                size_t out_pitch, size_t n);
+DH_API uint32_t dh_dvf_channels(const dh_dvf* h);
 DH_API int dh_dvf_reset(dh_dvf* h, void* stream);
 DH_API void dh_dvf_destroy(dh_dvf* h);
 
@@ -195,6 +209,7 @@ DH_API int dh_decoder_discard(dh_decoder* h, void* stream);
  * Record layout: {u8 kind, u8 slot, u8 a, u8 b, u8 data[12]}; DMR kinds: 1 slot reset, 2 set sync a (+ soft reset
  * if b), 3 soft reset, 4 link control (9 LC bytes in data), 5 talker-alias collector reset. */
 DH_API int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, size_t cap, size_t* len);
+DH_API uint32_t dh_decoder_channels(const dh_decoder* h);
 /* drops the accumulated host results */
 DH_API int dh_decoder_clear(dh_decoder* h);
 DH_API void dh_decoder_destroy(dh_decoder* h);
@@ -213,10 +228,19 @@ typedef struct dh_pipe dh_pipe;
 DH_API int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size_t max_chunk);
 /* n samples per channel from DEVICE memory (16-byte aligned, pitch % 4 == 0, pitch >= n rounded up to 4) */
 DH_API int dh_pipe_process_device(dh_pipe* h, const float* d_in, size_t in_pitch, size_t n, void* stream);
+/* int16 input (`csdr convert -i s16 -o float` fused into the RRC stage, see dh_rrc_process_s16): rows 16-byte
+ * aligned, pitch % 8 == 0, pitch >= n rounded up to 8.  DH_E_UNSUPPORTED for the pipes without an RRC stage. */
+DH_API int dh_pipe_process_device_s16(dh_pipe* h, const int16_t* d_in, size_t in_pitch, size_t n, void* stream);
+/* Records `event` (a cudaEvent_t) at the point where the most recent dh_pipe_process_device* call has finished
+ * reading its input block, so that a producer can reuse the block without waiting for the whole pipe. */
+DH_API int dh_pipe_input_event(dh_pipe* h, void* event);
+DH_API uint32_t dh_pipe_channels(const dh_pipe* h);
 /* n samples per channel from HOST memory (pinned memory makes the copy asynchronous); the host-to-device copy
  * is part of the call.  A pitch of dh_pipe_host_pitch() allows one contiguous transfer. */
 DH_API int dh_pipe_process_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n, void* stream);
+DH_API int dh_pipe_process_host_s16(dh_pipe* h, const int16_t* h_in, size_t in_pitch, size_t n, void* stream);
 DH_API size_t dh_pipe_host_pitch(const dh_pipe* h);
+DH_API size_t dh_pipe_host_pitch_s16(const dh_pipe* h);
 /* Streaming host interface: up to two steps in flight.  dh_pipe_submit_host starts the asynchronous upload of a
  * block from PINNED host memory (which must stay untouched until the step is collected) followed by the three
  * kernels on internal streams and returns at once; dh_pipe_collect_step waits for the OLDEST step in flight, reads
@@ -224,6 +248,7 @@ DH_API size_t dh_pipe_host_pitch(const dh_pipe* h);
  * kernels, read-back and metadata replay of step k.  Do not mix with dh_pipe_process_* on the same pipe while steps
  * are in flight.  DH_E_STATE when two steps are already in flight / nothing is in flight. */
 DH_API int dh_pipe_submit_host(dh_pipe* h, const float* h_in, size_t in_pitch, size_t n);
+DH_API int dh_pipe_submit_host_s16(dh_pipe* h, const int16_t* h_in, size_t in_pitch, size_t n);
 DH_API int dh_pipe_collect_step(dh_pipe* h);
 /* same contract as dh_decoder_collect */
 DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
@@ -259,6 +284,65 @@ DH_API uint64_t dh_pipe_launch_count(const dh_pipe* h);
 /* synchronous host copy of one channel's symbols of the last process call (test / debug helper) */
 DH_API int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t cap, size_t* count);
 DH_API void dh_pipe_destroy(dh_pipe* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * One pipe sharded over the GPUs of a node: one process (rank) per GPU, channels split into contiguous ranges
+ * (rank r of R owns [r*N/R, (r+1)*N/R), the first N % R ranks one channel more).  In the reference the same
+ * partitioning is "one shell pipe per channel" (examples/dmr-decoder.sh:12-23): channels never interact, so the only
+ * exchange steps are moving samples in and decoded frames out.  NCCL (>= 2.18, resolved at run time from the copy
+ * loaded in the process) carries both over NVLink:
+ *   scatter  the root (ingest) rank holds the block of ALL channels, every peer receives its rows;
+ *   gather   every rank packs its decoder results of the step (frames, metadata events, counts) into one wire block
+ *            and sends it to the root, which exposes all channels through dh_shard_output / dh_shard_meta.
+ * Steps are pipelined: scatter of step k+1, the kernels of step k and the gather of step k-1 overlap (three streams,
+ * two communicators); up to two steps may be in flight.  Every call below is COLLECTIVE: all ranks make the same
+ * sequence of create / submit / collect / discard calls with the same n and flags.
+ */
+typedef struct dh_shard dh_shard;
+
+#define DH_FMT_F32 0 /* float32 samples (what rrc_filter / fsk_demodulator read) */
+#define DH_FMT_S16 1 /* int16 samples; `csdr convert -i s16 -o float` is fused into the RRC stage */
+#define DH_SHARD_SCATTER 1 /* submit flag: d_in on the root covers all channels and is scattered */
+
+/* Bootstrap helpers for hosts without a communicator of their own (thin wrappers over ncclGetUniqueId /
+ * ncclCommInitRank): rank 0 creates the 128-byte id and hands it to the other ranks by any means. */
+DH_API int dh_shard_unique_id(uint8_t id[128]);
+DH_API int dh_shard_comm_init(void** comm, const uint8_t id[128], int rank, int world, int device);
+DH_API int dh_shard_comm_destroy(void* comm);
+/* the channel range [*lo, *hi) of a rank; host-only */
+DH_API int dh_shard_channel_range(uint64_t channels_total, int world, int rank, uint64_t* lo, uint64_t* hi);
+/* wire block of `channels` channels for steps of up to max_chunk samples: bytes / event records per channel slot and
+ * the size of the whole block; host-only */
+DH_API int dh_shard_wire_layout(int proto, size_t max_chunk, uint32_t channels, uint32_t* slot_bytes,
+                                uint32_t* slot_events, size_t* block_bytes);
+/* nccl_comm: an ncclComm_t spanning the `world` ranks (this process = `rank`, on GPU `device`); it stays owned by the
+ * caller and must outlive the shard.  root: the ingest + gathering rank.  world == 1 needs no communicator. */
+DH_API int dh_shard_create(dh_shard** out, void* nccl_comm, int rank, int world, int root, int device,
+                           uint64_t channels_total, int proto, size_t max_chunk, int sample_format);
+/* row pitch (in samples) every input block must use */
+DH_API size_t dh_shard_pitch(const dh_shard* h);
+DH_API uint32_t dh_shard_local_channels(const dh_shard* h);
+/* the pipe of this rank's channels (e.g. for dh_pipe_last_symbols / dh_decoder_set_slot_filter on its decoder) */
+DH_API dh_pipe* dh_shard_pipe(dh_shard* h);
+/* One step of n samples per channel, enqueued asynchronously.  With DH_SHARD_SCATTER the root passes the DEVICE block
+ * [channels_total][pitch] (produced on `stream`) and the other ranks pass NULL; without it every rank passes the
+ * block of its own channels.  The block must stay untouched until dh_shard_sync / the step is collected.
+ * DH_E_STATE when two steps are already in flight. */
+DH_API int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n, int flags, void* stream);
+/* Waits for the oldest step in flight.  On the root: reads the gathered wire blocks back and appends frames and
+ * metadata lines of ALL channels to the per-channel host buffers. */
+DH_API int dh_shard_collect_step(dh_shard* h);
+/* Retires the oldest step in flight without reading it back and without waiting (device-side throughput runs). */
+DH_API int dh_shard_discard_step(dh_shard* h);
+/* makes `stream` wait for everything enqueued so far */
+DH_API int dh_shard_sync(dh_shard* h, void* stream);
+/* root only: accumulated results of GLOBAL channel c; valid until the next collect / clear / destroy */
+DH_API int dh_shard_output(dh_shard* h, uint64_t channel, const uint8_t** data, size_t* len);
+DH_API int dh_shard_meta(dh_shard* h, uint64_t channel, const char** text, size_t* len);
+DH_API int dh_shard_clear(dh_shard* h);
+/* kernels launched by this rank (pipe + pack), bytes of its wire block per step, bytes read back by collect (root) */
+DH_API int dh_shard_stats(dh_shard* h, uint64_t* launches, uint64_t* wire_bytes_per_step, uint64_t* d2h_bytes);
+DH_API void dh_shard_destroy(dh_shard* h);
 
 #ifdef __cplusplus
 }

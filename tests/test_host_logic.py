@@ -100,6 +100,37 @@ def test_reciprocal_gain_exhaustive():
     assert int(out.strip()) == 0
 
 
+S16_SRC = r"""
+#include <stdio.h>
+#include <math.h>
+int main(void) {
+    int bad = 0;
+    volatile float r = 1.0f / 32767.0f;
+    for (int v = -32768; v < 32768; v++) {
+        float f = (float) v;
+        float ref = f / 32767.0f;                          /* csdr convert -i s16 -o float: (float) in / SHRT_MAX */
+        float q = f * r;                                   /* K1's s16_to_float (rrc.cu) */
+        float o = fmaf(fmaf(-q, 32767.0f, f), r, q);
+        if (o != ref || signbit(o) != signbit(ref)) bad++;
+    }
+    printf("%d\n", bad);
+    return 0;
+}
+"""
+
+
+def test_s16_conversion_exhaustive():
+    """The fused int16 -> float32 conversion of K1 (multiply by fl32(1/32767) + one fma refinement step) equals the
+    IEEE division `(float) s / 32767.0f` for all 65536 inputs."""
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "s16.c")
+        open(src, "w").write(S16_SRC)
+        exe = os.path.join(d, "s16")
+        subprocess.run(["gcc", "-O2", "-ffp-contract=off", src, "-o", exe, "-lm"], check=True)
+        out = subprocess.run([exe], stdout=subprocess.PIPE, text=True, check=True).stdout
+    assert int(out.strip()) == 0
+
+
 DIVC_SRC = r"""
 #include <stdio.h>
 #include <stdint.h>
