@@ -164,19 +164,52 @@ def proto_ids(name):
 
 def reference_arm(args, x_host_rows, cores):
     """Times the reference CPU modules (or the port when the compiled reference is absent) on host cores.
-    x_host_rows: float32 numpy [channels, n].  Returns (Msamples/s, kind, sample description, seconds/step)."""
+    x_host_rows: float32 numpy [channels, n]: one step's batch.  Runs args.warmup + args.steps steps unless the time
+    budget (--ref-budget seconds) ends the run earlier.  Returns (Msamples/s, kind, sample description, seconds per
+    step, steps timed, warm-up steps done)."""
     import oracle_lib
     orc = oracle_lib.best()
     nch, n = x_host_rows.shape
-    times = []
-    for it in range(args.warmup_ref + args.steps_ref):
+
+    def one():
         t0 = time.perf_counter()
         orc.pipe_batch(args.orc_proto, x_host_rows, threads=cores, chunk=4096)
-        dt = time.perf_counter() - t0
-        if it >= args.warmup_ref:
-            times.append(dt)
+        return time.perf_counter() - t0
+
+    dt0 = one()                                    # first warm-up step, also sizes the run
+    warm, steps = max(1, args.warmup), args.steps
+    if dt0 * (warm + steps) > args.ref_budget:     # a CPU loop needs no long warm-up; keep the timed steps
+        warm = 1
+        steps = max(1, min(steps, int(args.ref_budget / dt0) - 1))
+    for _ in range(warm - 1):
+        one()
+    times = [one() for _ in range(steps)]
     sec = sum(times) / len(times)
-    return nch * n / sec / 1e6, orc.kind, "%d channels x %d samples per step, %d step(s)" % (nch, n, len(times)), sec
+    return (nch * n / sec / 1e6, orc.kind, "%d channels x %d samples per step (the full per-GPU batch), %d step(s) timed"
+            % (nch, n, len(times)), sec, len(times), warm)
+
+
+def s16_conversion_seconds(x_host_rows, cores):
+    """`csdr convert -i s16 -o float` of one step's batch on all host cores (numpy releases the GIL): the extra CPU
+    work of the reference pipe when the ingest is int16 (reference examples/dmr-decoder.sh:13-15)."""
+    import numpy as np
+    from concurrent.futures import ThreadPoolExecutor
+    s = np.clip(np.rint(x_host_rows * 20000.0), -32768, 32767).astype(np.int16)
+    out = np.empty_like(x_host_rows)
+    parts = np.array_split(np.arange(s.shape[0]), max(1, cores))
+
+    def conv(idx):
+        if len(idx):
+            np.divide(s[idx[0]:idx[-1] + 1].astype(np.float32), np.float32(32767), out=out[idx[0]:idx[-1] + 1])
+
+    best = None
+    with ThreadPoolExecutor(max_workers=max(1, cores)) as ex:
+        for _ in range(3):
+            t0 = time.perf_counter()
+            list(ex.map(conv, parts))
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return best
 
 
 def bind_to_gpu_numa_node(local_rank):
@@ -214,6 +247,116 @@ def build_host_sample(workload, channels, n, seed):
     return x[:, :n].contiguous().numpy()
 
 
+def sharded_arm(args, dh, dist, dev, rank, world, stream, barrier, max_over_ranks, orc_proto):
+    """BASELINE configs[3]: `--shard-channels` (8192) channels per GPU, all blocks on rank 0, scatter -> compute ->
+    gather pipelined through dh_shard_*.  Returns the `nccl` object of the bench line (all ranks call this)."""
+    import numpy as np
+    import torch
+    from digiham_b200 import shard, synth
+    Cs, L = args.shard_channels, args.samples
+    total = Cs * world
+    out = {"channels_per_gpu": Cs, "channels_total": total, "samples_per_channel_per_step": L}
+    check_per_rank = 64
+    for fmt_name, fmt, dtype in (("f32", dh.FMT_F32, torch.float32), ("s16", dh.FMT_S16, torch.int16)):
+        sp = shard.ShardedPipe(total, dh.PROTO_DMR, max_chunk=L, device=dev, fmt=fmt)
+        pitch = sp.pitch
+        blocks = None
+        ref_rows = None
+        if rank == 0:
+            # two different steps' blocks for all channels (per-rank seeds differ, so a misplaced shard would show)
+            blocks = [torch.zeros((total, pitch), dtype=dtype, device=dev) for _ in range(2)]
+            ref_rows = []
+            for r in range(world):
+                xr = synth.dmr_channel_bank(Cs, 2 * L, seed=777 + r, device=dev)[0][:, :2 * L]
+                if fmt == dh.FMT_S16:
+                    xr = torch.clamp(torch.round(xr * 20000.0), -32768, 32767).to(torch.int16)
+                for k in range(2):
+                    blocks[k][r * Cs:(r + 1) * Cs, :L] = xr[:, k * L:(k + 1) * L]
+                head = xr[:check_per_rank].cpu().numpy()
+                ref_rows.append(head.astype(np.float32) / np.float32(32767) if fmt == dh.FMT_S16 else head)
+                del xr
+        # parity first, on the fresh streams: two steps through scatter / kernels / gather / read-back, then the
+        # gathered frames + metadata of the first `check_per_rank` channels of EVERY rank against the reference
+        sp.submit(blocks[0] if rank == 0 else None, L, scatter=True)
+        sp.submit(blocks[1] if rank == 0 else None, L, scatter=True)
+        sp.collect_step()
+        sp.collect_step()
+        parity = None
+        if rank == 0:
+            try:
+                import oracle_lib
+                orc = oracle_lib.best()
+                _, outs, metas = orc.pipe_batch(orc_proto, np.concatenate(ref_rows, axis=0), threads=os.cpu_count() or 1,
+                                                chunk=4096, meta_cap=1 << 15)
+                bad, nbytes = [], 0
+                for r in range(world):
+                    for c in range(check_per_rank):
+                        g = r * Cs + c
+                        i = r * check_per_rank + c
+                        nbytes += len(outs[i])
+                        if sp.output(g) != outs[i].tobytes() or sp.meta(g) != metas[i]:
+                            bad.append(g)
+                parity = {"checked_channels": world * check_per_rank, "per_rank": check_per_rank, "steps": 2,
+                          "reference_bytes": nbytes, "equal": not bad, "oracle": orc.kind}
+                if bad:
+                    parity["first_mismatches"] = bad[:8]
+            except Exception as ex:
+                parity = {"equal": None, "error": str(ex)}
+            sp.clear()
+        # timed loop: device-resident blocks on the ingest rank, results left in the gather buffers (discard)
+        def run(k):
+            for i in range(k):
+                sp.submit(blocks[i & 1] if rank == 0 else None, L, scatter=True)
+                sp.discard_step()
+            sp.sync()
+        run(max(3, args.warmup))
+        torch.cuda.synchronize()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(args.steps)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+        barrier()
+        # the same loop with the read-back + metadata replay of ALL channels on the ingest rank (wall clock)
+        k2 = max(2, min(args.steps, 10))
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        sp.submit(blocks[0] if rank == 0 else None, L, scatter=True)
+        for i in range(1, k2):
+            sp.submit(blocks[i & 1] if rank == 0 else None, L, scatter=True)
+            sp.collect_step()
+            if rank == 0:
+                sp.clear()
+        sp.collect_step()
+        sp.sync()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        launches, wire_bytes, _ = sp.stats()
+        esz = 2 if fmt == dh.FMT_S16 else 4
+        scatter_bytes = (world - 1) * Cs * pitch * esz
+        key = "" if fmt_name == "f32" else "_s16"
+        out["pipelined_value" + key] = total * L / (ms * 1e-3) / 1e6
+        out["pipelined_ms_per_step" + key] = ms
+        out["pipelined_collect_value" + key] = total * L * k2 / dt / 1e6
+        out["scatter_bytes_per_step" + key] = scatter_bytes
+        out["scatter_GBps_egress_if_bound" + key] = scatter_bytes / (ms * 1e-3) / 1e9
+        out["parity" + key] = parity
+        out["gather_wire_bytes_per_rank_per_step"] = wire_bytes
+        sp.close()
+        del blocks
+        torch.cuda.empty_cache()
+    out["unit"] = "Msamples/s"
+    out["note"] = ("dh_shard_*: rank 0 holds every channel's block in HBM; per step NCCL scatter (grouped send/recv) -> "
+                   "K1/K2/K3 on each rank -> pack -> NCCL gather to rank 0, consecutive steps overlapped on three streams "
+                   "and two communicators; both collectives inside the timed loop.  The ingest rank's NVLink egress "
+                   "bounds the step (scatter bytes / step time = scatter_GBps_egress_if_bound); `value` above is the "
+                   "same kernels with every rank's block already local")
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,6 +368,12 @@ def main():
     ap.add_argument("--channels", type=int, default=None, help="channels per GPU (default: the workload's)")
     ap.add_argument("--samples", type=int, default=SAMPLES_PER_STEP, help="samples per channel per step")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work budget of the cpu_baseline sample")
+    ap.add_argument("--ref-budget", type=float, default=150.0,
+                    help="--impl reference: wall-clock budget (s); fewer steps are timed when it would be exceeded")
+    ap.add_argument("--no-shard", action="store_true", help="N > 1: skip the sharded (scatter/gather) pipeline arm")
+    ap.add_argument("--shard-channels", type=int, default=8192,
+                    help="N > 1: channels per GPU of the sharded pipeline arm (BASELINE configs[3]: 65536 / 8)")
+    ap.add_argument("--wc", action="store_true", help="e2e arms: write-combined pinned host blocks")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-async", action="store_true",
@@ -244,23 +393,28 @@ def main():
                   args.channels, args.samples, args.workload.upper(), wl["desc"]),
               "channels_per_gpu": args.channels, "samples_per_channel_per_step": args.samples,
               "l2": "inputs larger than L2 (%.0f MB/step/GPU)" % (args.channels * args.samples * 4 / 1e6),
-              "sharding": "contiguous channel ranges per rank, no data-path collective"}
+              "sharding": "contiguous channel ranges per rank; `value`/`e2e`: every rank's block local, no data-path "
+                          "collective; N > 1 adds `nccl`: one ingest rank, NCCL scatter/gather pipelined (configs[3])"}
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample: enough channels for a few seconds of work on all cores
-        args.warmup_ref, args.steps_ref = min(args.warmup, 1), max(1, min(args.steps, 3))
-        nch = min(args.channels, 64 * cores)
-        x = build_host_sample(args.workload, nch, args.samples, seed=1234)
+        # the full per-GPU batch of the configuration (4096 channels x 48000 samples for the bench line), every step
+        x = build_host_sample(args.workload, args.channels, args.samples, seed=1234)
         args.orc_proto = proto_ids(args.workload)[1]
-        val, kind, sample, sec = reference_arm(args, x, cores)
-        line = {"metric": metric, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": args.steps_ref,
-                "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        val, kind, sample, sec, steps_done, warm_done = reference_arm(args, x, cores)
+        line = {"metric": metric, "value": val, "unit": "Msamples/s", "n_gpus": args.gpus, "steps": steps_done,
+                "warmup": warm_done, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference", "config": config,
                 "cpu_baseline": {"value": val, "unit": "Msamples/s", "cores": cores, "kind": kind, "sample": sample},
                 "e2e": {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        if wl["dominant"] == 0:
+            conv = s16_conversion_seconds(x, cores)
+            line["e2e_s16"] = {"value": args.channels * args.samples / (sec + conv) / 1e6, "unit": "Msamples/s",
+                               "convert_ms_per_step": conv * 1e3,
+                               "note": "int16 ingest: csdr convert -i s16 -o float (numpy float32 division on all cores) "
+                                       "in front of the same reference modules"}
         print(json.dumps(line))
         return
 
@@ -273,14 +427,22 @@ def main():
         raise SystemExit("bench.py: no CUDA device — the CUDA path is the only path (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    arm = {}     # how this arm ran (kept out of `config`, which both arms print identically)
     if world > 1:
-        config["numa"] = bind_to_gpu_numa_node(local_rank)
+        arm["numa"] = bind_to_gpu_numa_node(local_rank)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     C, L = args.channels, args.samples
     dh_proto, orc_proto = proto_ids(args.workload)
@@ -291,16 +453,16 @@ def main():
     sampler = ClockSampler(local_rank)
     # ---- kernel-level arm: batch resident in HBM ---------------------------------------------------------------
     # cross-step software pipelining (dh_pipe_set_async): K1 of step i+1 overlaps K2 + decoder of step i on two
-    # internal streams; every kernel of all K steps still runs inside the timed region (joined by pipe.sync)
+    # internal streams; every kernel of all K steps still runs inside the timed region (joined by pipe.sync).
+    # Per-stage timing events are OFF in the timed region; the stage times come from a second pass right after it.
     pipe.set_async(not args.no_async)
-    config["pipelining"] = ("none" if args.no_async or wl["dominant"] != 0 else
-                            "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)")
+    arm["pipelining"] = ("none" if args.no_async or wl["dominant"] != 0 else
+                         "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)")
     for _ in range(args.warmup):
         pipe.process(x, n=L)
         pipe.discard()
     pipe.sync()
     torch.cuda.synchronize()
-    pipe.set_profiling(True)
     launches0 = pipe.launch_count
     barrier()
     torch.cuda.synchronize()
@@ -315,39 +477,45 @@ def main():
     e1.record(stream)
     torch.cuda.synchronize()
     barrier()
-    ms_total = e0.elapsed_time(e1)
+    launches = pipe.launch_count - launches0
+    ms_step = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    value = world * C * L / (ms_step * 1e-3) / 1e6
+    # second pass, same schedule, with CUDA events around every kernel on its launching stream: K1's in-region time
+    prof_steps = min(args.steps, 50)
+    pipe.set_profiling(True)
+    for _ in range(prof_steps):
+        pipe.process(x, n=L)
+        pipe.discard()
+    pipe.sync()
+    torch.cuda.synchronize()
     stage_ms, calls = pipe.stage_times()
     pipe.set_async(False)
-    # the same kernels once more WITHOUT cross-step overlap (outside the timed region): K1's launch time with the
-    # SMs to itself, reported beside the in-region figure
+    # the same kernels once more WITHOUT cross-step overlap: K1's launch time with the SMs to itself
     iso_steps = 0 if args.no_async else min(10, args.steps)
     for _ in range(iso_steps):
         pipe.process(x, n=L)
         pipe.discard()
     iso_ms, iso_calls = pipe.stage_times() if iso_steps else ([0.0, 0.0, 0.0], 0)
     pipe.set_profiling(False)
-    launches = pipe.launch_count - launches0
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    ms_step = ms_total / args.steps
-    value = world * C * L / (ms_step * 1e-3) / 1e6
 
-    # ---- end-to-end arm: host buffers through the C ABI --------------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        pitch = pipe.host_pitch
-        xh = torch.empty((C, pitch), dtype=torch.float32).pin_memory()
-        xh.copy_(x[:, :pitch] if x.shape[1] >= pitch else torch.nn.functional.pad(x, (0, pitch - x.shape[1])))
-        _, d2h0 = pipe.decoder.stats()
-        # streaming host interface: two pinned blocks alternate; the upload of step k+1 overlaps kernels, read-back
-        # and metadata replay of step k (every byte of every step still crosses PCIe inside the timed region)
-        xh2 = torch.empty_like(xh).pin_memory()
-        xh2.copy_(xh)
-        bufs = [xh, xh2]
+    # ---- end-to-end arms: host buffers through the C ABI -------------------------------------------------------
+    def e2e_arm(dtype):
+        """dh_pipe_submit_host[_s16] / dh_pipe_collect_step with two pinned blocks alternating: the upload of step
+        k+1 overlaps kernels, read-back and metadata replay of step k; every byte of every step crosses PCIe inside
+        the timed region.  Returns the e2e object."""
+        s16 = dtype == torch.int16
+        pitch = pipe.host_pitch_s16 if s16 else pipe.host_pitch
+        esz = 2 if s16 else 4
+        src = x[:, :L]
+        if s16:
+            src = torch.clamp(torch.round(src * 20000.0), -32768, 32767).to(torch.int16)
+        blocks = [dh.PinnedBlock(C, pitch, dtype=dtype, write_combined=args.wc) for _ in range(2)]
+        for b in blocks:
+            b.tensor.zero_()
+            b.tensor[:, :L].copy_(src)
+        bufs = [b.tensor for b in blocks]
 
-        def e2e_steps(k):
+        def steps(k):
             pipe.submit(bufs[0], n=L)
             for i in range(1, k):
                 pipe.submit(bufs[i & 1], n=L)   # H2D + K1 + K2 + decoder kernel, asynchronous
@@ -356,84 +524,63 @@ def main():
             pipe.collect_step()
             pipe.decoder.clear()
 
-        e2e_steps(min(args.warmup, 3))
-        # the link itself: the same pinned block copied host -> device with nothing else going on
-        link = torch.empty((C, pitch), dtype=torch.float32, device=dev)
+        steps(min(args.warmup, 3))
+        # the link itself: the same pinned block copied host -> device with nothing else going on on this GPU, all
+        # ranks at the same time (barrier first), so the N > 1 figure is the CONCURRENT link ceiling of the box
+        link = torch.empty((C, pitch), dtype=dtype, device=dev)
         for _ in range(2):
-            link.copy_(xh, non_blocking=True)
+            link.copy_(bufs[0], non_blocking=True)
         torch.cuda.synchronize()
+        barrier()
         l0, l1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0.record(stream)
         for _ in range(5):
-            link.copy_(xh, non_blocking=True)
+            link.copy_(bufs[0], non_blocking=True)
         l1.record(stream)
         torch.cuda.synchronize()
-        link_ms = l0.elapsed_time(l1) / 5
+        link_ms = max_over_ranks(l0.elapsed_time(l1) / 5)
         del link
         _, d2h0 = pipe.decoder.stats()
         k_e2e = args.steps
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        e2e_steps(k_e2e)
+        steps(k_e2e)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        dt = max_over_ranks(time.perf_counter() - t0)
         barrier()
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t.item())
         _, d2h1 = pipe.decoder.stats()
-        e2e = {"value": world * C * L * k_e2e / dt / 1e6, "unit": "Msamples/s",
-               "h2d_bytes_per_step": C * pitch * 4, "d2h_bytes_per_step": (d2h1 - d2h0) // k_e2e,
-               "steps": k_e2e, "ms_per_step": dt / k_e2e * 1e3,
-               "h2d_copy_only": {"ms_per_step_block": link_ms, "GBps": C * pitch * 4 / link_ms / 1e6,
-                                 "Msamples_per_s": C * L / link_ms / 1e3,
-                                 "note": "pinned host -> device copy of one step's block alone: the PCIe ceiling of e2e"},
-               "path": "dh_pipe_submit_host (pinned H2D + 3 kernels) / dh_pipe_collect_step (D2H + metadata replay) per "
-                       "step, two steps in flight"}
+        for b in blocks:
+            b.close()
+        val = world * C * L * k_e2e / dt / 1e6
+        link_rate = world * C * L / link_ms / 1e3
+        return {"value": val, "unit": "Msamples/s", "h2d_bytes_per_step": C * pitch * esz,
+                "d2h_bytes_per_step": (d2h1 - d2h0) // k_e2e, "steps": k_e2e, "ms_per_step": dt / k_e2e * 1e3,
+                "host_sample_format": "int16 (csdr convert fused into K1)" if s16 else "float32",
+                "pinned": "write-combined" if args.wc else "default",
+                "h2d_copy_only": {"ms_per_step_block": link_ms, "GBps_per_gpu": C * pitch * esz / link_ms / 1e6,
+                                  "GBps_all_gpus": world * C * pitch * esz / link_ms / 1e6,
+                                  "Msamples_per_s": link_rate, "concurrent_ranks": world,
+                                  "note": "pinned host -> device copy of one step's block alone, all ranks at once "
+                                          "(max over ranks): the PCIe ceiling of e2e on this box"},
+                "frac_of_link": val / link_rate,
+                "path": "dh_pipe_submit_host%s (pinned H2D + 3 kernels) / dh_pipe_collect_step (D2H + metadata replay) "
+                        "per step, two steps in flight" % ("_s16" if s16 else "")}
+
+    e2e = e2e_s16 = None
+    if not args.no_e2e:
+        e2e = e2e_arm(torch.float32)
+        if wl["dominant"] == 0:          # pipes with an RRC stage take int16 samples
+            e2e_s16 = e2e_arm(torch.int16)
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- N > 1: the two optional collectives (input scatter from an ingest rank, frame gather), measured apart ----
+    # ---- N > 1: the sharded pipeline of BASELINE configs[3] ------------------------------------------------------
+    # One ingest rank holds the blocks of ALL channels; per step: NCCL scatter -> K1/K2/K3 on every rank -> pack ->
+    # NCCL gather of frames + metadata events to the ingest rank, the three phases of consecutive steps overlapping
+    # (dh_shard_*, digiham_b200/csrc/shard.cu).  Both collectives are INSIDE the timed loop.
     nccl = None
-    if world > 1:
-        from digiham_b200 import shard
-        pitch = x.shape[1]
-        x_all = x.repeat(world, 1) if rank == 0 else None           # ingest rank holds every rank's block
-        for _ in range(2):
-            xs = shard.scatter_channels(x_all, world * C, pitch, device=dev)
-        torch.cuda.synchronize()
-        barrier()
-        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        s0.record(stream)
-        for _ in range(reps):
-            xs = shard.scatter_channels(x_all, world * C, pitch, device=dev)
-        s1.record(stream)
-        torch.cuda.synchronize()
-        t = torch.tensor([s0.elapsed_time(s1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        scatter_ms = float(t.item())
-        del x_all
-        # one step on the scattered block, then gather the decoded frames + metadata on rank 0
-        pipe.process(xs, n=L)
-        pipe.collect()
-        frames = [pipe.output(c) for c in range(C)]
-        metas = [pipe.meta(c) for c in range(C)]
-        pipe.decoder.clear()
-        shard.gather_frames(frames[:8] + [b""] * (C - 8), world * C, device=dev)   # connection set-up is not the gather
-        torch.cuda.synchronize()
-        barrier()
-        t0 = time.perf_counter()
-        gf = shard.gather_frames(frames, world * C, device=dev)
-        gm = shard.gather_frames(metas, world * C, device=dev)
-        torch.cuda.synchronize()
-        gather_s = time.perf_counter() - t0
-        nccl = {"scatter_ms_per_step": scatter_ms,
-                "scatter_GBps_egress": (world - 1) * C * pitch * 4 / (scatter_ms * 1e-3) / 1e9,
-                "gather_ms_per_step": gather_s * 1e3,
-                "gathered_bytes": (sum(len(f) for f in gf) + sum(len(m) for m in gm)) if rank == 0 else None,
-                "note": "collectives are off the compute path: channels never interact (SURVEY.md 8e)"}
+    if world > 1 and not args.no_shard and args.workload == "dmr":
+        nccl = sharded_arm(args, dh, dist, dev, rank, world, stream, barrier, max_over_ranks, orc_proto)
 
     if rank != 0:
         if world > 1:
@@ -442,10 +589,10 @@ def main():
 
     # ---- roofline of the dominant kernel (K1) ------------------------------------------------------------------
     peak, peak_src = peaks()
-    # stage sums cover every (sub-)chunk launch of the timed region; per step = / steps
+    # stage sums cover every launch of the profiled pass; per step = / prof_steps
     dom = wl["dominant"]
     algo_bytes = wl["algo"]
-    k1_ms = stage_ms[dom] / args.steps           # launch time of the dominant kernel (K1, or K2 for the FSK pipes)
+    k1_ms = stage_ms[dom] / prof_steps           # launch time of the dominant kernel (K1, or K2 for the FSK pipes)
     achieved = C * L * algo_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
@@ -470,13 +617,14 @@ def main():
                 "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
                 "not_overlapped": iso,
                 "algorithmic_bytes_per_sample": algo_bytes,
-                "ms_per_launch": k1_ms * args.steps / max(1, calls), "k1_ms_per_step": k1_ms,
-                "stage_ms_per_step": {"k1_rrc": stage_ms[0] / args.steps, "k2_demod": stage_ms[1] / args.steps,
-                                      "k3_k4_dmr": stage_ms[2] / args.steps,
-                                      "launches_per_stage_per_step": calls / args.steps,
-                                      "note": "per-kernel CUDA events on the launching streams; with cross-step "
-                                              "pipelining K1 of step i+1 runs beside K2/K3 of step i, so the sum "
-                                              "exceeds ms_per_step"},
+                "ms_per_launch": k1_ms * prof_steps / max(1, calls), "k1_ms_per_step": k1_ms,
+                "stage_ms_per_step": {"k1_rrc": stage_ms[0] / prof_steps, "k2_demod": stage_ms[1] / prof_steps,
+                                      "k3_k4_dmr": stage_ms[2] / prof_steps,
+                                      "launches_per_stage_per_step": calls / prof_steps, "profiled_steps": prof_steps,
+                                      "note": "per-kernel CUDA events on the launching streams, taken in a second pass "
+                                              "of the same pipelined schedule right after the timed region (the "
+                                              "timed region itself records no per-stage events); K1 of step i+1 runs "
+                                              "beside K2/K3 of step i, so the sum exceeds ms_per_step"},
                 "fp32_issue_bound": {"note": "K1 executes 162 separately rounded fp32 ops/sample (no FMA, bit-exact); "
                                              "the binding ceiling is FP32 issue, not HBM (SURVEY.md D9)",
                                      "fp32_ops_per_s": C * L * (322 if args.workload == "nxdn" else 162) / (k1_ms * 1e-3)
@@ -520,7 +668,9 @@ def main():
     line = {"metric": metric, "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu}
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "arm": arm}
+    if e2e_s16:
+        line["e2e_s16"] = e2e_s16
     if nccl:
         line["nccl"] = nccl
     print(json.dumps(line))

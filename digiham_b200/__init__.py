@@ -17,6 +17,7 @@ from ._capi import (  # noqa: F401
     DecoderBank,
     Pipe,
     DvfBank,
+    PinnedBlock,
     PROTO_DMR,
     PROTO_YSF,
     PROTO_POCSAG,
@@ -29,4 +30,4 @@ from ._capi import (  # noqa: F401
     SHARD_SCATTER,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "PROTO_NXDN", "PROTO_DSTAR", "RRC_WIDE", "RRC_NARROW", "FMT_F32", "FMT_S16", "SHARD_SCATTER"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PinnedBlock", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "PROTO_NXDN", "PROTO_DSTAR", "RRC_WIDE", "RRC_NARROW", "FMT_F32", "FMT_S16", "SHARD_SCATTER"]

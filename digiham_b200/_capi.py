@@ -102,6 +102,11 @@ def lib():
     L.dh_decoder_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
     L.dh_pipe_destroy.restype = None
+    L.dh_test_fec.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    L.dh_test_bptc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
+    L.dh_test_viterbi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_host_alloc.argtypes = [c_void_pp, ctypes.c_size_t, ctypes.c_int]
+    L.dh_host_free.argtypes = [ctypes.c_void_p]
     L.dh_rrc_process_s16.argtypes = L.dh_rrc_process.argtypes
     L.dh_pipe_process_device_s16.argtypes = L.dh_pipe_process_device.argtypes
     L.dh_pipe_process_host_s16.argtypes = L.dh_pipe_process_host.argtypes
@@ -162,6 +167,29 @@ def _stream_ptr(stream):
 def _dev_index(device):
     d = torch.device(device)
     return d.index if d.index is not None else torch.cuda.current_device()
+
+
+class PinnedBlock:
+    """A page-locked host block from dh_host_alloc, viewed as a torch tensor [rows, pitch] (`.tensor`)."""
+
+    def __init__(self, rows, pitch, dtype=torch.float32, write_combined=False):
+        self._p = ctypes.c_void_p()
+        self.nbytes = int(rows) * int(pitch) * torch.empty((), dtype=dtype).element_size()
+        check(lib().dh_host_alloc(ctypes.byref(self._p), self.nbytes, int(write_combined)))
+        buf = (ctypes.c_char * self.nbytes).from_address(self._p.value)
+        self.tensor = torch.frombuffer(buf, dtype=dtype).view(int(rows), int(pitch))
+
+    def close(self):
+        if self._p:
+            self.tensor = None
+            lib().dh_host_free(self._p)
+            self._p = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def pitch4(n):

@@ -32,6 +32,19 @@ const char* dh_last_error(void) { return dh::g_error; }
 
 const char* dh_version(void) { return "0.1.0-b200"; }
 
+int dh_host_alloc(void** ptr, size_t bytes, int write_combined) {
+    DH_REQUIRE(ptr != nullptr && bytes > 0, DH_E_INVALID, "dh_host_alloc: bad argument");
+    *ptr = nullptr;
+    DH_CUDA(cudaHostAlloc(ptr, bytes, cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0)));
+    return DH_OK;
+}
+
+int dh_host_free(void* ptr) {
+    if (!ptr) return DH_OK;
+    DH_CUDA(cudaFreeHost(ptr));
+    return DH_OK;
+}
+
 int dh_device_count(int* count) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);

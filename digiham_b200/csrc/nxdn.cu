@@ -14,6 +14,7 @@
 //   * a TX_RELEASE FACCH1 returns to SyncPhase WITHOUT consuming its own 72 symbols (nxdn_phase.cpp:149-152);
 //   * the LICH of the last valid frame is kept when a new LICH fails its parity (nxdn_phase.cpp:64-69).
 #include "decoder_ops.hpp"
+#include "test_hooks.hpp"
 #include "viterbi.cuh"
 #include "crc_par.cuh"
 
@@ -370,5 +371,41 @@ const ProtoOps kNxdnOps = {"nxdn", sizeof(NxdnState), kNxCarryCap, nxdn_init_sta
 }  // namespace
 
 const ProtoOps* nxdn_ops() { return &kNxdnOps; }
+
+// ---- device-level test hook (dh_test_viterbi variants 2 / 3) ------------------------------------------------------
+namespace {
+
+template <int STEPS>
+__global__ void nxdn_test_viterbi_kernel(const uint8_t* dibits, uint32_t n, uint32_t* words, uint32_t* metric) {
+    constexpr int NW = (STEPS + 31) / 32;
+    __shared__ uint8_t stage[4][96];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t i = blockIdx.x * 4 + wib;
+    if (i >= n) return;
+    for (int k = lane; k < STEPS; k += 32) stage[wib][k] = dibits[(size_t) i * STEPS + k];
+    __syncwarp();
+    uint32_t w[NW];
+    const uint32_t m = viterbi<STEPS, true>(stage[wib], lane, w);
+    if (lane == 0) {
+        for (int k = 0; k < NW; k++) words[(size_t) i * NW + k] = w[k];
+        metric[i] = m;
+    }
+}
+
+}  // namespace
+
+namespace test {
+
+int nxdn_viterbi(int steps, const uint8_t* d_dibits, uint32_t n, uint32_t* d_words, uint32_t* d_metric, cudaStream_t st) {
+    DH_REQUIRE(steps == 36 || steps == 96, DH_E_INVALID, "dh_test_viterbi: NXDN decodes 36 or 96 steps");
+    if (n == 0) return DH_OK;
+    const unsigned grid = (n + 3) / 4;
+    if (steps == 36) nxdn_test_viterbi_kernel<36><<<grid, 128, 0, st>>>(d_dibits, n, d_words, d_metric);
+    else nxdn_test_viterbi_kernel<96><<<grid, 128, 0, st>>>(d_dibits, n, d_words, d_metric);
+    DH_CUDA(cudaGetLastError());
+    return DH_OK;
+}
+
+}  // namespace test
 
 }  // namespace dh

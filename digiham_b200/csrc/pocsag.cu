@@ -10,6 +10,7 @@
 // Warp-parallel pieces: the sync correlator tests 32 bit offsets per step (bit-plane by __ballot_sync, window by
 // __funnelshift_r, XOR + __popc against the frame sync word 0x7CD215D8); a codeword is gathered with one ballot.
 #include "decoder_ops.hpp"
+#include "test_hooks.hpp"
 
 #define DH_TABLES_NO_HOST_ARRAYS
 #include "tables.inc"
@@ -42,6 +43,18 @@ __constant__ uint32_t c_bch_h[10] = DH_BCH_31_21_H_INIT;
 
 // frame sync word, transmitted MSB first (pocsag_phase.hpp:15); plane bit i = i-th received bit
 constexpr uint32_t kFsc = 0x7CD215D8u;
+// bch_31_21 (bch_31_21.c:521-561) on the 31 code bits of a codeword (parity bit already shifted out): syndrome ->
+// direct LUT of the 1- and 2-bit error patterns; false when the syndrome is not in the table
+__device__ __forceinline__ bool fec_bch31(uint32_t& payload) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < 10; k++) s = (s << 1) | parity32(c_bch_h[k] & payload);
+    if (s == 0) return true;
+    const uint32_t e = c_bch_lut[s];
+    payload ^= e;
+    return e != 0;
+}
+
 __host__ __device__ constexpr uint32_t bit_reverse(uint32_t v) {
     uint32_t r = 0;
     for (int i = 0; i < 32; i++) r |= ((v >> i) & 1u) << (31 - i);
@@ -193,15 +206,7 @@ __global__ void __launch_bounds__(kPWarps * 32) pocsag_kernel(const __grid_const
             } else {
                 uint32_t cw = __brev(plane);   // first received bit = MSB
                 uint32_t payload = cw >> 1;
-                uint32_t s = 0;
-#pragma unroll
-                for (int k = 0; k < 10; k++) s = (s << 1) | parity32(c_bch_h[k] & payload);
-                bool ok = true;
-                if (s != 0) {
-                    const uint32_t e = c_bch_lut[s];
-                    payload ^= e;
-                    ok = e != 0;
-                }
+                bool ok = fec_bch31(payload);
                 cw = (cw & 1u) | (payload << 1);
                 if (ok && parity32(cw)) ok = false;
                 if (ok) {
@@ -265,5 +270,30 @@ const ProtoOps kPocsagOps = {"pocsag", sizeof(PocsagState), kPocsagCarryCap, poc
 }  // namespace
 
 const ProtoOps* pocsag_ops() { return &kPocsagOps; }
+
+// ---- device-level test hook (dh_test_fec code 7) -------------------------------------------------------------------
+namespace {
+
+__global__ void pocsag_test_bch_kernel(uint32_t* words, uint8_t* ok, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w = words[i];
+    const bool r = fec_bch31(w);
+    words[i] = w;
+    ok[i] = r ? 1 : 0;
+}
+
+}  // namespace
+
+namespace test {
+
+int pocsag_bch(uint32_t* d_words, uint8_t* d_ok, uint32_t n, cudaStream_t st) {
+    if (n == 0) return DH_OK;
+    pocsag_test_bch_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_words, d_ok, n);
+    DH_CUDA(cudaGetLastError());
+    return DH_OK;
+}
+
+}  // namespace test
 
 }  // namespace dh

@@ -13,6 +13,7 @@
 // register exchange, the whole decoded bit string travels with the state — word by word through __shfl_sync.
 // Metrics are kept modulo 256 like the reference's uint8_t (trellis.c:28,68).
 #include "decoder_ops.hpp"
+#include "test_hooks.hpp"
 #include "viterbi.cuh"
 #include "crc_par.cuh"
 
@@ -479,5 +480,66 @@ const ProtoOps kYsfOps = {"ysf", sizeof(YsfState), kYsfCarryCap, ysf_init_states
 }  // namespace
 
 const ProtoOps* ysf_ops() { return &kYsfOps; }
+
+// ---- device-level test hooks (dh_test_fec code 6, dh_test_viterbi variants 0 / 1) --------------------------------
+namespace {
+
+__global__ void ysf_test_golay24_kernel(uint32_t* words, uint8_t* ok, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w = words[i];
+    const bool r = fec_golay24(w);
+    words[i] = w;
+    ok[i] = r ? 1 : 0;
+}
+
+// one warp decodes inputs 2w and 2w + 1 side by side, exactly like ysf_frame does (viterbi_pair)
+template <int STEPS>
+__global__ void ysf_test_viterbi_kernel(const uint8_t* dibits, uint32_t n, uint32_t* words, uint32_t* metric) {
+    constexpr int NW = (STEPS + 31) / 32;
+    __shared__ uint8_t stage[4][2][192];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t a = (blockIdx.x * 4 + wib) * 2, b = a + 1;
+    if (a >= n) return;
+    const uint32_t bb = b < n ? b : a;
+    for (int i = lane; i < STEPS; i += 32) {
+        stage[wib][0][i] = dibits[(size_t) a * STEPS + i];
+        stage[wib][1][i] = dibits[(size_t) bb * STEPS + i];
+    }
+    __syncwarp();
+    uint32_t wa[NW], wb[NW], ma, mb;
+    viterbi_pair<STEPS, false>(stage[wib][0], stage[wib][1], lane, wa, wb, ma, mb);
+    if (lane == 0) {
+        for (int k = 0; k < NW; k++) {
+            words[(size_t) a * NW + k] = wa[k];
+            if (b < n) words[(size_t) b * NW + k] = wb[k];
+        }
+        metric[a] = ma;
+        if (b < n) metric[b] = mb;
+    }
+}
+
+}  // namespace
+
+namespace test {
+
+int ysf_golay24(uint32_t* d_words, uint8_t* d_ok, uint32_t n, cudaStream_t st) {
+    if (n == 0) return DH_OK;
+    ysf_test_golay24_kernel<<<(n + 255) / 256, 256, 0, st>>>(d_words, d_ok, n);
+    DH_CUDA(cudaGetLastError());
+    return DH_OK;
+}
+
+int ysf_viterbi(int steps, const uint8_t* d_dibits, uint32_t n, uint32_t* d_words, uint32_t* d_metric, cudaStream_t st) {
+    DH_REQUIRE(steps == 100 || steps == 180, DH_E_INVALID, "dh_test_viterbi: YSF decodes 100 or 180 steps");
+    if (n == 0) return DH_OK;
+    const unsigned grid = ((n + 1) / 2 + 3) / 4;
+    if (steps == 100) ysf_test_viterbi_kernel<100><<<grid, 128, 0, st>>>(d_dibits, n, d_words, d_metric);
+    else ysf_test_viterbi_kernel<180><<<grid, 128, 0, st>>>(d_dibits, n, d_words, d_metric);
+    DH_CUDA(cudaGetLastError());
+    return DH_OK;
+}
+
+}  // namespace test
 
 }  // namespace dh

@@ -56,6 +56,11 @@ DH_API const char* dh_last_error(void);
 DH_API const char* dh_version(void);
 /* number of CUDA devices visible to the library; DH_E_NODEVICE if there is none */
 DH_API int dh_device_count(int* count);
+/* Page-locked host blocks for the streaming host interfaces (dh_pipe_submit_host*): cudaHostAlloc, portable across
+ * devices.  write_combined != 0 requests write-combined memory: faster to upload on some hosts, very slow to READ
+ * from the CPU — only for blocks the host fills sequentially and never reads back. */
+DH_API int dh_host_alloc(void** ptr, size_t bytes, int write_combined);
+DH_API int dh_host_free(void* ptr);
 /* frees the device staging the *_process_host variants cached for a bank handle (call before destroying it) */
 DH_API void dh_host_scratch_release(const void* handle);
 
@@ -343,6 +348,24 @@ DH_API int dh_shard_clear(dh_shard* h);
 /* kernels launched by this rank (pipe + pack), bytes of its wire block per step, bytes read back by collect (root) */
 DH_API int dh_shard_stats(dh_shard* h, uint64_t* launches, uint64_t* wire_bytes_per_step, uint64_t* d2h_bytes);
 DH_API void dh_shard_destroy(dh_shard* h);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Test hooks: the DEVICE implementations of the FEC primitives, one word / block / trellis input per element, for
+ * exhaustive comparison with the reference's C functions.  Host buffers, current device, synchronous.
+ *   dh_test_fec  code 0 hamming_7_4 (src/dmr_decoder/hamming_7_4.c:40-72), 1 hamming_13_9 (hamming_13_9.c:52-84),
+ *                2 hamming_15_11 (hamming_15_11.c:56-88), 3 hamming_16_11 (hamming_16_11.c:61-93),
+ *                4 quadratic_residue (quadratic_residue.c:302-335), 5 golay_20_8 (golay_20_8.c:1403-1435),
+ *                6 golay_24_12 (src/ysf_decoder/golay_24_12.c:2383-2415), 7 bch_31_21
+ *                (src/pocsag_decoder/bch_31_21.c:521-561): words are corrected in place, ok[i] = return value.
+ *   dh_test_bptc bptc_196_96 (src/dmr_decoder/bptc_196_96.c:5-59): payload [n][25] bytes -> out [n][12], ok[n].
+ *   dh_test_viterbi variant 0 / 1: decode_trellis with 100 / 180 steps (src/ysf_decoder/trellis.c:32-109);
+ *                variant 2 / 3: Nxdn::Trellis::decode with 36 / 96 steps (src/nxdn_decoder/trellis.cpp:29-101).
+ *                dibits [n][steps], one received dibit per byte; words [n][(steps + 31) / 32] decoded bits MSB first;
+ *                metric [n] the winning path metric (uint8 / uint16 arithmetic like the references).
+ */
+DH_API int dh_test_fec(int code, uint32_t* h_words, uint8_t* h_ok, uint32_t n);
+DH_API int dh_test_bptc(const uint8_t* h_payload, uint8_t* h_out, uint8_t* h_ok, uint32_t n);
+DH_API int dh_test_viterbi(int variant, const uint8_t* h_dibits, uint32_t n, uint32_t* h_words, uint32_t* h_metric);
 
 #ifdef __cplusplus
 }

@@ -98,6 +98,13 @@ int orc_nxdn_facch1(const uint8_t in[72]);
  * Header::toString() in text (NUL-terminated, truncated at cap). */
 int orc_dstar_header(const uint8_t in[660], char* text, size_t cap);
 
+/* Batched forms (batch.inc): loops over the single-item functions above on nthreads host threads.
+ * orc_trellis_batch: in [n][in_stride] packed dibits, out [n][out_stride]; nxdn != 0 runs orc_nxdn_trellis. */
+void orc_fec_batch(int code, uint32_t* words, uint8_t* ok, size_t n, int nthreads);
+void orc_bptc_batch(const uint8_t* in, uint8_t* out, uint8_t* ok, size_t n, int nthreads);
+void orc_trellis_batch(int nxdn, const uint8_t* in, size_t in_stride, unsigned steps, uint8_t* out, size_t out_stride,
+                       unsigned* metric, size_t n, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

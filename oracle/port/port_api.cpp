@@ -2,6 +2,7 @@
 // `chunk` is accepted and ignored: the reference's results do not depend on how the stream is cut as long as the
 // modules are drained after every chunk (asserted on the compiled reference in tests/test_oracle_cpu.py), and the
 // restatement always works on the whole stream.
+#include <algorithm>
 #include "../oracle_api.h"
 #include "port.hpp"
 
@@ -135,3 +136,5 @@ int orc_nxdn_facch1(const uint8_t in[72]) { return port::nxdn_facch1_probe(in); 
 int orc_dstar_header(const uint8_t in[660], char* text, size_t cap) { return port::dstar_header_probe(in, text, cap); }
 
 }
+
+#include "../batch.inc"

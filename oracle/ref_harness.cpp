@@ -7,6 +7,7 @@
 //     compiled with `-include zero_heap.hpp` (malloc -> calloc) and the module objects themselves are
 //     placement-constructed into zeroed storage; global operator new below is zero-filling as well.
 //   * chunking: modules are always drained with `while (canProcess()) process();` (src/lib/cli.cpp:29-33).
+#include <algorithm>
 #include "oracle_api.h"
 
 #include "rrc_filter.hpp"
@@ -437,3 +438,5 @@ int orc_dstar_header(const uint8_t in[660], char* text, size_t cap) {
 }
 
 }
+
+#include "batch.inc"

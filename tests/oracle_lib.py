@@ -55,6 +55,13 @@ def _bind(path):
     L.orc_whitening.restype = None
     L.orc_hamming_distance.restype = ctypes.c_uint
     L.orc_hamming_distance.argtypes = [_vp, _vp, _sz]
+    if hasattr(L, "orc_fec_batch"):
+        L.orc_fec_batch.restype = None
+        L.orc_fec_batch.argtypes = [ctypes.c_int, _vp, _vp, _sz, ctypes.c_int]
+        L.orc_bptc_batch.restype = None
+        L.orc_bptc_batch.argtypes = [_vp, _vp, _vp, _sz, ctypes.c_int]
+        L.orc_trellis_batch.restype = None
+        L.orc_trellis_batch.argtypes = [ctypes.c_int, _vp, _sz, ctypes.c_uint, _vp, _sz, _vp, _sz, ctypes.c_int]
     if hasattr(L, "orc_nxdn_trellis"):
         L.orc_nxdn_trellis.restype = ctypes.c_uint
         L.orc_nxdn_trellis.argtypes = [_vp, ctypes.c_uint, _vp]
@@ -142,6 +149,35 @@ class Oracle:
         w = ctypes.c_uint32(int(word))
         ok = self.L.orc_fec(code, ctypes.byref(w))
         return bool(ok), w.value
+
+    def fec_batch(self, code, words, threads=8):
+        """words: uint32 array -> (ok uint8 array, corrected uint32 array)."""
+        w = np.ascontiguousarray(words, dtype=np.uint32).copy()
+        ok = np.zeros(w.size, dtype=np.uint8)
+        self.L.orc_fec_batch(code, w.ctypes.data, ok.ctypes.data, w.size, threads)
+        return ok, w
+
+    def bptc_batch(self, payloads, threads=8):
+        """payloads: [n, 25] uint8 -> (ok [n], out [n, 12])."""
+        p = np.ascontiguousarray(payloads, dtype=np.uint8)
+        out = np.zeros((p.shape[0], 12), dtype=np.uint8)
+        ok = np.zeros(p.shape[0], dtype=np.uint8)
+        self.L.orc_bptc_batch(p.ctypes.data, out.ctypes.data, ok.ctypes.data, p.shape[0], threads)
+        return ok, out
+
+    def trellis_batch(self, dibits, nxdn=False, threads=8):
+        """dibits: [n, steps] one dibit per byte -> (metric [n], decoded bytes [n, ceil(steps / 8)], MSB first)."""
+        d = np.ascontiguousarray(dibits, dtype=np.uint8) & 3
+        n, steps = d.shape
+        pad = (-steps) % 4
+        dp = np.concatenate([d, np.zeros((n, pad), dtype=np.uint8)], axis=1).reshape(n, -1, 4)
+        packed = np.ascontiguousarray((dp[:, :, 0] << 6) | (dp[:, :, 1] << 4) | (dp[:, :, 2] << 2) | dp[:, :, 3]).astype(np.uint8)
+        out_stride = (steps + 7) // 8 + 2
+        out = np.zeros((n, out_stride), dtype=np.uint8)
+        metric = np.zeros(n, dtype=np.uint32)
+        self.L.orc_trellis_batch(int(nxdn), packed.ctypes.data, packed.shape[1], steps, out.ctypes.data, out_stride,
+                                 metric.ctypes.data, n, threads)
+        return metric, out[:, :(steps + 7) // 8]
 
     def fec_syndrome(self, code, word):
         return self.L.orc_fec_syndrome(code, int(word))
