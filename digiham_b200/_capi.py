@@ -102,6 +102,12 @@ def lib():
     L.dh_decoder_discard.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
     L.dh_pipe_destroy.argtypes = [ctypes.c_void_p]
     L.dh_pipe_destroy.restype = None
+    for bank in ("rrc", "demod", "decoder", "pipe"):
+        getattr(L, "dh_%s_state_size" % bank).argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_size_t)]
+        getattr(L, "dh_%s_state_export" % bank).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                            ctypes.POINTER(ctypes.c_size_t), ctypes.c_void_p]
+        getattr(L, "dh_%s_state_import" % bank).argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                                            ctypes.c_void_p]
     L.dh_test_fec.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
     L.dh_test_bptc.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32]
     L.dh_test_viterbi.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
@@ -192,6 +198,19 @@ class PinnedBlock:
             pass
 
 
+def _export_state(bank, handle, stream=None):
+    n = ctypes.c_size_t()
+    check(getattr(lib(), "dh_%s_state_size" % bank)(handle, ctypes.byref(n)))
+    buf = ctypes.create_string_buffer(n.value)
+    w = ctypes.c_size_t()
+    check(getattr(lib(), "dh_%s_state_export" % bank)(handle, buf, n.value, ctypes.byref(w), _stream_ptr(stream)))
+    return buf.raw[:w.value]
+
+
+def _import_state(bank, handle, blob, stream=None):
+    check(getattr(lib(), "dh_%s_state_import" % bank)(handle, blob, len(blob), _stream_ptr(stream)))
+
+
 def pitch4(n):
     return (int(n) + 3) & ~3
 
@@ -228,6 +247,13 @@ class RrcBank:
 
     def reset(self, stream=None):
         check(lib().dh_rrc_reset(self._h, _stream_ptr(stream)))
+
+    def export_state(self, stream=None):
+        """The bank's per-channel state as an opaque bytes blob (dh_rrc_state_export)."""
+        return _export_state("rrc", self._h, stream)
+
+    def import_state(self, blob, stream=None):
+        _import_state("rrc", self._h, blob, stream)
 
     def close(self):
         if self._h:
@@ -285,6 +311,13 @@ class DemodBank:
 
     def reset(self, stream=None):
         check(lib().dh_demod_reset(self._h, _stream_ptr(stream)))
+
+    def export_state(self, stream=None):
+        """The bank's per-channel state as an opaque bytes blob (dh_demod_state_export)."""
+        return _export_state("demod", self._h, stream)
+
+    def import_state(self, blob, stream=None):
+        _import_state("demod", self._h, blob, stream)
 
     def close(self):
         if self._h:
@@ -361,6 +394,13 @@ class DecoderBank:
 
     def clear(self):
         check(lib().dh_decoder_clear(self._h))
+
+    def export_state(self, stream=None):
+        """The bank's per-channel state as an opaque bytes blob (dh_decoder_state_export)."""
+        return _export_state("decoder", self._h, stream)
+
+    def import_state(self, blob, stream=None):
+        _import_state("decoder", self._h, blob, stream)
 
     def close(self):
         if self._h:
@@ -474,6 +514,13 @@ class Pipe:
 
     def totals(self):
         return self.decoder.totals()
+
+    def export_state(self, stream=None):
+        """The bank's per-channel state as an opaque bytes blob (dh_pipe_state_export)."""
+        return _export_state("pipe", self._h, stream)
+
+    def import_state(self, blob, stream=None):
+        _import_state("pipe", self._h, blob, stream)
 
     def close(self):
         if self._h:

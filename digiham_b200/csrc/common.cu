@@ -3,6 +3,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstring>
 
 namespace dh {
 
@@ -22,6 +23,19 @@ int sm_count(int device) {
         return 148;
     }
     return n;
+}
+
+int check_state_header(const void* blob, size_t bytes, const StateHeader& want, const char* who) {
+    DH_REQUIRE(blob != nullptr && bytes >= sizeof(StateHeader), DH_E_INVALID, "%s: blob too small for a state header", who);
+    StateHeader got;
+    memcpy(&got, blob, sizeof(got));
+    DH_REQUIRE(got.magic == kStateMagic && got.version == kStateVersion, DH_E_INVALID,
+               "%s: not a state blob of this library version", who);
+    DH_REQUIRE(got.kind == want.kind && got.channels == want.channels && memcmp(got.cfg, want.cfg, sizeof(got.cfg)) == 0,
+               DH_E_INVALID, "%s: the blob belongs to a different bank (kind %u/%u, channels %u/%u, configuration)", who,
+               got.kind, want.kind, got.channels, want.channels);
+    DH_REQUIRE(bytes >= sizeof(StateHeader) + got.payload, DH_E_INVALID, "%s: truncated blob", who);
+    return DH_OK;
 }
 
 }  // namespace dh

@@ -48,6 +48,36 @@ struct DeviceGuard {
 
 int sm_count(int device);
 
+// ---- per-channel state blobs (dh_*_state_export / _import) ---------------------------------------------------------
+// Every blob starts with this header; import refuses a blob whose kind / channel count / configuration words differ
+// from the bank it is loaded into.
+struct StateHeader {
+    uint32_t magic;      // 'DHST'
+    uint32_t version;
+    uint32_t kind;       // 1 RRC, 2 demodulator, 3 decoder, 4 pipe
+    uint32_t channels;
+    uint32_t cfg[4];     // bank configuration (taps / sps / protocol ...)
+    uint64_t payload;    // bytes that follow the header
+};
+constexpr uint32_t kStateMagic = 0x54534844u;
+constexpr uint32_t kStateVersion = 1;
+inline StateHeader make_state_header(uint32_t kind, uint32_t channels, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                     uint64_t payload) {
+    StateHeader h;
+    h.magic = kStateMagic;
+    h.version = kStateVersion;
+    h.kind = kind;
+    h.channels = channels;
+    h.cfg[0] = c0;
+    h.cfg[1] = c1;
+    h.cfg[2] = c2;
+    h.cfg[3] = c3;
+    h.payload = payload;
+    return h;
+}
+// DH_OK when `blob` is a state blob of exactly this configuration
+int check_state_header(const void* blob, size_t bytes, const StateHeader& want, const char* who);
+
 // ---- device-side PTX helpers (TMA 1-D bulk copies + mbarrier) -------------------------------------------------
 #ifdef __CUDACC__
 

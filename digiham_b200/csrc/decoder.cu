@@ -7,7 +7,9 @@
 #include <algorithm>
 #include <cstring>
 #include <new>
+#include <string>
 #include <thread>
+#include <utility>
 #include <vector>
 
 using dh::DecEvent;
@@ -321,6 +323,101 @@ int dh_meta_replay(int proto, const void* events, uint32_t n_events, char* out, 
 }
 
 uint32_t dh_decoder_channels(const dh_decoder* h) { return h ? h->channels : 0; }
+
+// ---- state: per-channel phase state + unconsumed symbol tails (device), slot filters and the metadata collectors
+// (host).  Results that were decoded but not collected yet are not part of the state: collect first.
+static dh::StateHeader decoder_header(const dh_decoder* h, uint64_t payload) {
+    return dh::make_state_header(3, h->channels, (uint32_t) h->proto, (uint32_t) h->ops->state_size,
+                                 (uint32_t) h->ops->carry_cap, 0, payload);
+}
+
+static void decoder_replay_blobs(const dh_decoder* h, std::string& blob) {
+    for (uint32_t c = 0; c < h->channels; c++) {
+        std::string one;
+        if (h->sink.replay[c]) h->sink.replay[c]->save(one);
+        const uint32_t n = (uint32_t) one.size();
+        blob.append(reinterpret_cast<const char*>(&n), sizeof(n));
+        blob.append(one);
+    }
+}
+
+int dh_decoder_state_size(const dh_decoder* h, size_t* bytes) {
+    DH_REQUIRE(h != nullptr && bytes != nullptr, DH_E_INVALID, "dh_decoder_state_size: NULL argument");
+    std::string blob;
+    decoder_replay_blobs(h, blob);
+    *bytes = sizeof(dh::StateHeader) + (size_t) h->channels * (h->ops->state_size + (size_t) h->ops->carry_cap + 1) +
+             blob.size();
+    return DH_OK;
+}
+
+int dh_decoder_state_export(dh_decoder* h, void* h_buf, size_t cap, size_t* written, void* stream) {
+    DH_REQUIRE(h != nullptr && h_buf != nullptr, DH_E_INVALID, "dh_decoder_state_export: NULL argument");
+    std::string blob;
+    decoder_replay_blobs(h, blob);
+    const size_t dev_bytes = (size_t) h->channels * (h->ops->state_size + (size_t) h->ops->carry_cap);
+    const dh::StateHeader hd = decoder_header(h, dev_bytes + h->channels + blob.size());
+    DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_decoder_state_export: buffer too small");
+    dh::DeviceGuard guard(h->device);
+    int rc = decoder_reserve(h, h->max_syms ? h->max_syms : 16);
+    if (rc != DH_OK) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    char* out = static_cast<char*>(h_buf);
+    std::memcpy(out, &hd, sizeof(hd));
+    out += sizeof(hd);
+    DH_CUDA(cudaMemcpyAsync(out, h->d_states, (size_t) h->channels * h->ops->state_size, cudaMemcpyDeviceToHost, st));
+    out += (size_t) h->channels * h->ops->state_size;
+    DH_CUDA(cudaMemcpy2DAsync(out, h->ops->carry_cap, h->d_sym, h->sym_pitch, h->ops->carry_cap, h->channels,
+                              cudaMemcpyDeviceToHost, st));
+    out += (size_t) h->channels * h->ops->carry_cap;
+    DH_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(out, h->h_slot_filter.data(), h->channels);
+    out += h->channels;
+    std::memcpy(out, blob.data(), blob.size());
+    if (written) *written = sizeof(hd) + hd.payload;
+    return DH_OK;
+}
+
+int dh_decoder_state_import(dh_decoder* h, const void* h_buf, size_t bytes, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_state_import: handle is NULL");
+    const size_t dev_bytes = (size_t) h->channels * (h->ops->state_size + (size_t) h->ops->carry_cap);
+    dh::StateHeader hd = decoder_header(h, 0);
+    int rc = dh::check_state_header(h_buf, bytes, hd, "dh_decoder_state_import");
+    if (rc != DH_OK) return rc;
+    std::memcpy(&hd, h_buf, sizeof(hd));
+    DH_REQUIRE(hd.payload >= dev_bytes + h->channels, DH_E_INVALID, "dh_decoder_state_import: truncated blob");
+    // host part first (it can fail on a malformed blob before anything on the device changes)
+    const uint8_t* in = static_cast<const uint8_t*>(h_buf) + sizeof(hd);
+    const uint8_t* end = in + hd.payload;
+    const uint8_t* p = in + dev_bytes + h->channels;
+    std::vector<std::pair<const uint8_t*, uint32_t>> parts(h->channels);
+    for (uint32_t c = 0; c < h->channels; c++) {
+        uint32_t n = 0;
+        DH_REQUIRE((size_t) (end - p) >= sizeof(n), DH_E_INVALID, "dh_decoder_state_import: truncated collector state");
+        std::memcpy(&n, p, sizeof(n));
+        p += sizeof(n);
+        DH_REQUIRE((size_t) (end - p) >= n, DH_E_INVALID, "dh_decoder_state_import: truncated collector state");
+        parts[c] = {p, n};
+        p += n;
+    }
+    for (uint32_t c = 0; c < h->channels; c++) {
+        if (!h->sink.replay[c]) continue;
+        DH_REQUIRE(h->sink.replay[c]->load(parts[c].first, parts[c].second), DH_E_INVALID,
+                   "dh_decoder_state_import: malformed collector state of channel %u", c);
+    }
+    dh::DeviceGuard guard(h->device);
+    rc = decoder_reserve(h, h->max_syms ? h->max_syms : 16);
+    if (rc != DH_OK) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    DH_CUDA(cudaMemcpyAsync(h->d_states, in, (size_t) h->channels * h->ops->state_size, cudaMemcpyHostToDevice, st));
+    in += (size_t) h->channels * h->ops->state_size;
+    DH_CUDA(cudaMemcpy2DAsync(h->d_sym, h->sym_pitch, in, h->ops->carry_cap, h->ops->carry_cap, h->channels,
+                              cudaMemcpyHostToDevice, st));
+    in += (size_t) h->channels * h->ops->carry_cap;
+    DH_CUDA(cudaStreamSynchronize(st));
+    std::memcpy(h->h_slot_filter.data(), in, h->channels);
+    h->filter_dirty = true;
+    return DH_OK;
+}
 
 void dh_decoder_destroy(dh_decoder* h) {
     if (!h) return;

@@ -24,6 +24,8 @@
 // alternating work-row sets.
 #include "common.cuh"
 
+#include <cstring>
+
 #include <cfloat>
 #include <type_traits>
 #include <cstdlib>
@@ -687,6 +689,59 @@ int dh_demod_reset(dh_demod* h, void* stream) {
 }
 
 uint32_t dh_demod_channels(const dh_demod* h) { return h ? h->channels : 0; }
+
+// ---- state: ChannelState of every channel + the unconsumed sample tails (columns [0, carry_cap) of the work rows) --
+static dh::StateHeader demod_header(const dh_demod* h) {
+    const uint64_t payload = (uint64_t) h->channels * (sizeof(ChannelState) + (size_t) h->carry_cap * sizeof(float));
+    return dh::make_state_header(2, h->channels, (uint32_t) h->sps, (uint32_t) h->four_level, (uint32_t) h->invert,
+                                 (uint32_t) h->carry_cap, payload);
+}
+
+int dh_demod_state_size(const dh_demod* h, size_t* bytes) {
+    DH_REQUIRE(h != nullptr && bytes != nullptr, DH_E_INVALID, "dh_demod_state_size: NULL argument");
+    *bytes = sizeof(dh::StateHeader) + demod_header(h).payload;
+    return DH_OK;
+}
+
+int dh_demod_state_export(dh_demod* h, void* h_buf, size_t cap, size_t* written, void* stream) {
+    DH_REQUIRE(h != nullptr && h_buf != nullptr, DH_E_INVALID, "dh_demod_state_export: NULL argument");
+    const dh::StateHeader hd = demod_header(h);
+    DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_demod_state_export: buffer too small");
+    dh::DeviceGuard guard(h->device);
+    int rc = demod_reserve(h, 0);
+    if (rc != DH_OK) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    char* out = static_cast<char*>(h_buf);
+    std::memcpy(out, &hd, sizeof(hd));
+    out += sizeof(hd);
+    DH_CUDA(cudaMemcpyAsync(out, h->d_state, (size_t) h->channels * sizeof(ChannelState), cudaMemcpyDeviceToHost, st));
+    out += (size_t) h->channels * sizeof(ChannelState);
+    const size_t w = (size_t) h->carry_cap * sizeof(float);
+    DH_CUDA(cudaMemcpy2DAsync(out, w, h->d_work[h->cur], h->pitch * sizeof(float), w, h->channels, cudaMemcpyDeviceToHost,
+                              st));
+    DH_CUDA(cudaStreamSynchronize(st));
+    if (written) *written = sizeof(hd) + hd.payload;
+    return DH_OK;
+}
+
+int dh_demod_state_import(dh_demod* h, const void* h_buf, size_t bytes, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_state_import: handle is NULL");
+    const dh::StateHeader hd = demod_header(h);
+    int rc = dh::check_state_header(h_buf, bytes, hd, "dh_demod_state_import");
+    if (rc != DH_OK) return rc;
+    dh::DeviceGuard guard(h->device);
+    rc = demod_reserve(h, 0);
+    if (rc != DH_OK) return rc;
+    cudaStream_t st = (cudaStream_t) stream;
+    const char* in = static_cast<const char*>(h_buf) + sizeof(hd);
+    DH_CUDA(cudaMemcpyAsync(h->d_state, in, (size_t) h->channels * sizeof(ChannelState), cudaMemcpyHostToDevice, st));
+    in += (size_t) h->channels * sizeof(ChannelState);
+    const size_t w = (size_t) h->carry_cap * sizeof(float);
+    DH_CUDA(cudaMemcpy2DAsync(h->d_work[h->cur], h->pitch * sizeof(float), in, w, w, h->channels, cudaMemcpyHostToDevice,
+                              st));
+    DH_CUDA(cudaStreamSynchronize(st));
+    return DH_OK;
+}
 
 void dh_demod_destroy(dh_demod* h) {
     if (!h) return;

@@ -21,6 +21,10 @@ std::string serialize(const std::map<std::string, std::string>& kv);
 
 void MetaReplay::emit(const std::map<std::string, std::string>& kv, std::string& out) {
     out += serialize(kv);
+    emit_kv_only(kv);
+}
+
+void MetaReplay::emit_kv_only(const std::map<std::string, std::string>& kv) {
     if (kv_sink) {
         auto put16 = [&](size_t v) {
             kv_sink->push_back((char) (v & 0xFF));
@@ -100,13 +104,10 @@ struct TalkerAlias {
     bool hasHeader() const { return blocks & 1u; }
     unsigned format() const { return data[0] >> 6; }
     unsigned length() const { return (data[0] & 0x3E) >> 1; }
+    // bytes available without a gap: 7 per block, counting the blocks received contiguously from block 0
     unsigned collectedBytes() const {
-        int i;
-        for (i = 0; i < 4; i++) {
-            const unsigned mask = (1u << (i + 1)) - 1;
-            if ((blocks & mask) != mask) break;
-        }
-        return (unsigned) i * 7;
+        const unsigned leading = (unsigned) __builtin_ctz(~blocks & 0x1Fu);   // trailing one-bits of the block mask
+        return (leading < 4 ? leading : 4) * 7;
     }
     std::string contents() const {
         if (!hasHeader()) return "";
@@ -219,9 +220,34 @@ class DmrReplay: public MetaReplay {
                 flush(s, out);
             }
         }
+        void save(std::string& blob) const override {
+            StateWriter w{blob};
+            const_cast<DmrReplay*>(this)->fields(w);
+        }
+        bool load(const uint8_t* data, size_t len) override {
+            StateReader r{data, data + len};
+            fields(r);
+            return r.ok && r.p == r.end;
+        }
     private:
         DmrSlot slots[2];
         TalkerAlias ta[2];
+
+        template <class A> void fields(A& a) {
+            for (int s = 0; s < 2; s++) {
+                a.val(slots[s].dirty);
+                a.val(slots[s].sync);
+                a.val(slots[s].type);
+                a.val(slots[s].source);
+                a.val(slots[s].target);
+                a.str(slots[s].alias);
+                a.val(slots[s].hasCoord);
+                a.val(slots[s].lat);
+                a.val(slots[s].lon);
+                a.pod(ta[s].data, sizeof(ta[s].data));
+                a.val(ta[s].blocks);
+            }
+        }
 
         void handleLc(int s, const uint8_t* lc) {
             const unsigned opcode = lc[0] & 0x3F;
@@ -320,6 +346,15 @@ class YsfReplay: public MetaReplay {
                 }
             }
         }
+        void save(std::string& blob) const override {
+            StateWriter w{blob};
+            const_cast<YsfReplay*>(this)->fields(w);
+        }
+        bool load(const uint8_t* data, size_t len) override {
+            StateReader r{data, data + len};
+            fields(r);
+            return r.ok && r.p == r.end;
+        }
     private:
         std::string mode, destination, source, up, down;
         bool hasCoord = false;
@@ -328,6 +363,21 @@ class YsfReplay: public MetaReplay {
         bool dirty = false;
         unsigned dcNext = 0;
         unsigned char dcData[20] = {0};
+
+        template <class A> void fields(A& a) {
+            a.str(mode);
+            a.str(destination);
+            a.str(source);
+            a.str(up);
+            a.str(down);
+            a.val(hasCoord);
+            a.val(lat);
+            a.val(lon);
+            a.val(held);
+            a.val(dirty);
+            a.val(dcNext);
+            a.pod(dcData, sizeof(dcData));
+        }
 
         void send(std::string& out) {
             if (held) {
@@ -469,11 +519,29 @@ class NxdnReplay: public MetaReplay {
                 }
             }
         }
+        void save(std::string& blob) const override {
+            StateWriter w{blob};
+            const_cast<NxdnReplay*>(this)->fields(w);
+        }
+        bool load(const uint8_t* data, size_t len) override {
+            StateReader r{data, data + len};
+            fields(r);
+            return r.ok && r.p == r.end;
+        }
     private:
         std::string sync, type;
         unsigned source = 0, destination = 0;
         int held = 0;
         bool dirty = false;
+
+        template <class A> void fields(A& a) {
+            a.str(sync);
+            a.str(type);
+            a.val(source);
+            a.val(destination);
+            a.val(held);
+            a.val(dirty);
+        }
 
         void send(std::string& out) {
             if (held) {
@@ -529,6 +597,15 @@ class DstarReplay: public MetaReplay {
                 }
             }
         }
+        void save(std::string& blob) const override {
+            StateWriter w{blob};
+            const_cast<DstarReplay*>(this)->fields(w);
+        }
+        bool load(const uint8_t* data, size_t len) override {
+            StateReader r{data, data + len};
+            fields(r);
+            return r.ok && r.p == r.end;
+        }
     private:
         std::string sync, message, departure, destination, ourCall, yourCall, dprs;
         bool located = false;
@@ -541,6 +618,27 @@ class DstarReplay: public MetaReplay {
         unsigned char hdr[41] = {0};
         unsigned hdrCount = 0;
         std::string simpleData;
+
+        template <class A> void fields(A& a) {
+            a.str(sync);
+            a.str(message);
+            a.str(departure);
+            a.str(destination);
+            a.str(ourCall);
+            a.str(yourCall);
+            a.str(dprs);
+            a.val(located);
+            a.val(lat);
+            a.val(lon);
+            a.val(held);
+            a.val(dirty);
+            a.pod(radioHeader, sizeof(radioHeader));
+            a.pod(msg, sizeof(msg));
+            a.val(msgBlocks);
+            a.pod(hdr, sizeof(hdr));
+            a.val(hdrCount);
+            a.str(simpleData);
+        }
 
         void send(std::string& out) {
             if (held) {
@@ -697,9 +795,38 @@ class DstarReplay: public MetaReplay {
         }
 };
 
+// ---- POCSAG ------------------------------------------------------------------------------------------------------
+// Pocsag::Decoder has no MetaCollector: a finished Message hands its {address, message} map to the decoder's
+// Serializer and the rendered text goes to the OUTPUT writer (reference src/pocsag_decoder/message.cpp:16-24).  The
+// bank renders with the default StringSerializer on the device; for callers with another Serializer the kernel also
+// leaves one event per message — {record length, number of address digits} — from which the structured map is cut
+// out of the byte stream here (no separator search: message bodies may contain ';', ':' and newlines).
+class PocsagReplay: public MetaReplay {
+    public:
+        void apply(const DecEvent*, uint32_t, std::string&) override {}
+        void apply_with_output(const DecEvent* ev, uint32_t n, const uint8_t* bytes, size_t nbytes, std::string&) override {
+            if (!kv_sink) return;
+            size_t pos = 0;
+            for (uint32_t i = 0; i < n; i++) {
+                if (ev[i].kind != 1) continue;
+                const size_t len = ev[i].data[0] | (size_t) ev[i].data[1] << 8;
+                const size_t digits = ev[i].a;
+                if (pos + len > nbytes || len < 8 + digits + 9 + 1) break;
+                std::map<std::string, std::string> kv;
+                kv["address"] = std::string(reinterpret_cast<const char*>(bytes + pos + 8), digits);
+                kv["message"] = std::string(reinterpret_cast<const char*>(bytes + pos + 8 + digits + 9), len - (8 + digits + 9) - 1);
+                emit_kv_only(kv);
+                pos += len;
+            }
+        }
+        void save(std::string&) const override {}
+        bool load(const uint8_t*, size_t len) override { return len == 0; }
+};
+
 }  // namespace
 
 MetaReplay* make_dstar_replay() { return new DstarReplay(); }
+MetaReplay* make_pocsag_replay() { return new PocsagReplay(); }
 MetaReplay* make_nxdn_replay() { return new NxdnReplay(); }
 MetaReplay* make_dmr_replay() { return new DmrReplay(); }
 MetaReplay* make_ysf_replay() { return new YsfReplay(); }

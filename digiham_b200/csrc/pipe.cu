@@ -12,6 +12,7 @@
 #include "common.cuh"
 
 #include <cstdlib>
+#include <cstring>
 #include <new>
 #include <vector>
 
@@ -450,6 +451,86 @@ int dh_pipe_collect(dh_pipe* h, void* stream) {
 }
 
 dh_decoder* dh_pipe_decoder(dh_pipe* h) { return h ? h->decoder : nullptr; }
+
+// ---- state of the whole pipe: the blobs of its stages back to back behind a pipe header ----------------------------
+int dh_pipe_state_size(const dh_pipe* h, size_t* bytes) {
+    DH_REQUIRE(h != nullptr && bytes != nullptr, DH_E_INVALID, "dh_pipe_state_size: NULL argument");
+    size_t total = sizeof(dh::StateHeader), part = 0;
+    int rc = DH_OK;
+    if (h->rrc) {
+        rc = dh_rrc_state_size(h->rrc, &part);
+        if (rc != DH_OK) return rc;
+        total += part;
+    }
+    rc = dh_demod_state_size(h->demod, &part);
+    if (rc != DH_OK) return rc;
+    total += part;
+    rc = dh_decoder_state_size(h->decoder, &part);
+    if (rc != DH_OK) return rc;
+    *bytes = total + part;
+    return DH_OK;
+}
+
+int dh_pipe_state_export(dh_pipe* h, void* h_buf, size_t cap, size_t* written, void* stream) {
+    DH_REQUIRE(h != nullptr && h_buf != nullptr, DH_E_INVALID, "dh_pipe_state_export: NULL argument");
+    DH_REQUIRE(h->submitted == h->collected, DH_E_STATE, "dh_pipe_state_export: steps are in flight, collect them first");
+    int rc = dh_pipe_sync(h, stream);   // asynchronous mode: the stages run on internal streams
+    if (rc != DH_OK) return rc;
+    DH_REQUIRE(cap >= sizeof(dh::StateHeader), DH_E_INVALID, "dh_pipe_state_export: buffer too small");
+    char* out = static_cast<char*>(h_buf) + sizeof(dh::StateHeader);
+    size_t left = cap - sizeof(dh::StateHeader), n = 0;
+    if (h->rrc) {
+        rc = dh_rrc_state_export(h->rrc, out, left, &n, stream);
+        if (rc != DH_OK) return rc;
+        out += n;
+        left -= n;
+    }
+    rc = dh_demod_state_export(h->demod, out, left, &n, stream);
+    if (rc != DH_OK) return rc;
+    out += n;
+    left -= n;
+    rc = dh_decoder_state_export(h->decoder, out, left, &n, stream);
+    if (rc != DH_OK) return rc;
+    out += n;
+    const size_t total = (size_t) (out - static_cast<char*>(h_buf));
+    const dh::StateHeader hd = dh::make_state_header(4, h->channels, (uint32_t) h->proto, 0, 0, 0, total - sizeof(hd));
+    std::memcpy(h_buf, &hd, sizeof(hd));
+    if (written) *written = total;
+    return DH_OK;
+}
+
+int dh_pipe_state_import(dh_pipe* h, const void* h_buf, size_t bytes, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_state_import: handle is NULL");
+    DH_REQUIRE(h->submitted == h->collected, DH_E_STATE, "dh_pipe_state_import: steps are in flight, collect them first");
+    const dh::StateHeader want = dh::make_state_header(4, h->channels, (uint32_t) h->proto, 0, 0, 0, 0);
+    int rc = dh::check_state_header(h_buf, bytes, want, "dh_pipe_state_import");
+    if (rc != DH_OK) return rc;
+    rc = dh_pipe_sync(h, stream);
+    if (rc != DH_OK) return rc;
+    const char* in = static_cast<const char*>(h_buf) + sizeof(dh::StateHeader);
+    size_t left = bytes - sizeof(dh::StateHeader);
+    auto part_size = [&](size_t* n) -> int {
+        DH_REQUIRE(left >= sizeof(dh::StateHeader), DH_E_INVALID, "dh_pipe_state_import: truncated blob");
+        dh::StateHeader hd;
+        std::memcpy(&hd, in, sizeof(hd));
+        *n = sizeof(hd) + hd.payload;
+        DH_REQUIRE(left >= *n, DH_E_INVALID, "dh_pipe_state_import: truncated blob");
+        return DH_OK;
+    };
+    size_t n = 0;
+    if (h->rrc) {
+        if ((rc = part_size(&n)) != DH_OK) return rc;
+        if ((rc = dh_rrc_state_import(h->rrc, in, n, stream)) != DH_OK) return rc;
+        in += n;
+        left -= n;
+    }
+    if ((rc = part_size(&n)) != DH_OK) return rc;
+    if ((rc = dh_demod_state_import(h->demod, in, n, stream)) != DH_OK) return rc;
+    in += n;
+    left -= n;
+    if ((rc = part_size(&n)) != DH_OK) return rc;
+    return dh_decoder_state_import(h->decoder, in, n, stream);
+}
 
 int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, const uint32_t** d_nsym) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_last_symbols: handle is NULL");

@@ -95,14 +95,27 @@ __device__ void serialize_message(PCtx& c) {
         for (int i = 0; i < 9; i++) put((uint8_t) k2[i]);
         for (int i = 0; i < kMaxMessage && c.content[i]; i++) put(c.content[i]);
         put('\n');
-        // broadcast the length through the content scratch? no: recompute below
+        // hand the record length to the other lanes through the scratch behind the message buffer
         c.content[kMaxMessage] = (uint8_t) (n & 0xFF);
         c.content[kMaxMessage + 1] = (uint8_t) (n >> 8);
     }
     __syncwarp();
     const uint32_t n = c.content[kMaxMessage] | ((uint32_t) c.content[kMaxMessage + 1] << 8);
-    if (c.w.out_len + n <= c.w.out_cap) c.w.out_len += n;
-    else c.w.flags |= kFlagOutOverflow;
+    if (c.w.out_len + n <= c.w.out_cap) {
+        c.w.out_len += n;
+        // record boundary for callers with their own Serializer: {length of the rendered record, address digits}, so
+        // that the host can slice {address, message} out of the byte stream without searching for separators
+        uint32_t a = c.st.msg_address;
+        uint8_t nd = 0;
+        do {
+            nd++;
+            a /= 10u;
+        } while (a);
+        const uint8_t rec[2] = {(uint8_t) (n & 0xFF), (uint8_t) (n >> 8)};
+        c.w.event(c.lane, 1, 0, nd, 0, rec, 2);
+    } else {
+        c.w.flags |= kFlagOutOverflow;
+    }
     __syncwarp();
 }
 
@@ -255,7 +268,8 @@ void pocsag_init_states(void* host_states, uint32_t count) {
 }
 // shortest message = address + one message codeword (64 bits) -> about 27 bytes of text
 uint32_t pocsag_out_bytes(size_t max_syms) { return (uint32_t) ((max_syms + kPocsagCarryCap) / 2 + 256); }
-uint32_t pocsag_events(size_t) { return 1; }
+// one record-boundary event per serialised message (address + at least one message codeword = 64 bits)
+uint32_t pocsag_events(size_t max_syms) { return (uint32_t) ((max_syms + kPocsagCarryCap) / 64 + 4); }
 
 int pocsag_launch(const DecIo& io, void* d_states, const uint8_t*, cudaStream_t stream) {
     const unsigned grid = (io.channels + kPWarps - 1) / kPWarps;
@@ -265,7 +279,7 @@ int pocsag_launch(const DecIo& io, void* d_states, const uint8_t*, cudaStream_t 
 }
 
 const ProtoOps kPocsagOps = {"pocsag", sizeof(PocsagState), kPocsagCarryCap, pocsag_init_states, pocsag_out_bytes,
-                             pocsag_events, pocsag_launch, nullptr};
+                             pocsag_events, pocsag_launch, make_pocsag_replay};
 
 }  // namespace
 

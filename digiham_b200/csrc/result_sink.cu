@@ -88,7 +88,7 @@ int ResultSink::ingest(const uint32_t* d_counts, const uint8_t* d_out, size_t ou
             if (ev_len[c] && rp) {
                 const size_t before = r.meta.size();
                 rp->kv_sink = &r.meta_kv;
-                rp->apply(h_ev + (size_t) c * max_ev, ev_len[c], r.meta);
+                rp->apply_with_output(h_ev + (size_t) c * max_ev, ev_len[c], h_out + (size_t) c * max_out, out_len[c], r.meta);
                 sums[1] += r.meta.size() - before;
             }
         }

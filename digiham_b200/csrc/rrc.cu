@@ -455,6 +455,49 @@ int dh_rrc_set_tile_preference(dh_rrc* h, int prefer_small) {
     return DH_OK;
 }
 
+// ---- state: the FIR history (the last nZeros inputs of every channel) ----------------------------------------------
+namespace {
+dh::StateHeader rrc_header(const dh_rrc* h) {
+    uint32_t g[2];
+    std::memcpy(g, &h->gain, sizeof(g));
+    return dh::make_state_header(1, h->channels, (uint32_t) h->nz, (uint32_t) h->mul_recip, g[0], g[1],
+                                 (uint64_t) h->channels * h->nz * sizeof(float));
+}
+}  // namespace
+
+int dh_rrc_state_size(const dh_rrc* h, size_t* bytes) {
+    DH_REQUIRE(h != nullptr && bytes != nullptr, DH_E_INVALID, "dh_rrc_state_size: NULL argument");
+    *bytes = sizeof(dh::StateHeader) + (size_t) h->channels * h->nz * sizeof(float);
+    return DH_OK;
+}
+
+int dh_rrc_state_export(dh_rrc* h, void* h_buf, size_t cap, size_t* written, void* stream) {
+    DH_REQUIRE(h != nullptr && h_buf != nullptr, DH_E_INVALID, "dh_rrc_state_export: NULL argument");
+    const dh::StateHeader hd = rrc_header(h);
+    DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_rrc_state_export: buffer too small");
+    dh::DeviceGuard guard(h->device);
+    std::memcpy(h_buf, &hd, sizeof(hd));
+    const float* cur = h->d_hist + (size_t) h->cur * h->channels * h->nz;
+    DH_CUDA(cudaMemcpyAsync(static_cast<char*>(h_buf) + sizeof(hd), cur, hd.payload, cudaMemcpyDeviceToHost,
+                            (cudaStream_t) stream));
+    DH_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    if (written) *written = sizeof(hd) + hd.payload;
+    return DH_OK;
+}
+
+int dh_rrc_state_import(dh_rrc* h, const void* h_buf, size_t bytes, void* stream) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_state_import: handle is NULL");
+    const dh::StateHeader hd = rrc_header(h);
+    int rc = dh::check_state_header(h_buf, bytes, hd, "dh_rrc_state_import");
+    if (rc != DH_OK) return rc;
+    dh::DeviceGuard guard(h->device);
+    float* cur = h->d_hist + (size_t) h->cur * h->channels * h->nz;
+    DH_CUDA(cudaMemcpyAsync(cur, static_cast<const char*>(h_buf) + sizeof(hd), hd.payload, cudaMemcpyHostToDevice,
+                            (cudaStream_t) stream));
+    DH_CUDA(cudaStreamSynchronize((cudaStream_t) stream));
+    return DH_OK;
+}
+
 int dh_rrc_reset(dh_rrc* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_reset: handle is NULL");
     dh::DeviceGuard guard(h->device);

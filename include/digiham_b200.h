@@ -291,6 +291,29 @@ DH_API int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, si
 DH_API void dh_pipe_destroy(dh_pipe* h);
 
 /* ------------------------------------------------------------------------------------------------------------
+ * Per-channel state as opaque blobs (checkpoint / migration of running channels).  In the reference the state of
+ * a channel is the member data of its module instances (delay line: src/rrc_filter/rrc_filter.cpp:5-10; rings and
+ * offsets: include/gfsk_demodulator.hpp:20-33; phase + collectors: include/decoder.hpp:24-29); here it lives in HBM
+ * (plus the host-side metadata collectors of a decoder bank).  export writes header + state into a HOST buffer of
+ * at least *_state_size bytes (synchronises `stream`); import loads a blob into a bank of the SAME configuration
+ * (kind, channel count, taps / sps / protocol: DH_E_INVALID otherwise), after which the bank continues the stream
+ * exactly where the exporting bank stopped.  Decoded results that were not collected yet are not part of the state.
+ * The dh_pipe_* forms bundle the blobs of the pipe's stages (the pipe must have no step in flight).
+ */
+DH_API int dh_rrc_state_size(const dh_rrc* h, size_t* bytes);
+DH_API int dh_rrc_state_export(dh_rrc* h, void* h_buf, size_t cap, size_t* written, void* stream);
+DH_API int dh_rrc_state_import(dh_rrc* h, const void* h_buf, size_t bytes, void* stream);
+DH_API int dh_demod_state_size(const dh_demod* h, size_t* bytes);
+DH_API int dh_demod_state_export(dh_demod* h, void* h_buf, size_t cap, size_t* written, void* stream);
+DH_API int dh_demod_state_import(dh_demod* h, const void* h_buf, size_t bytes, void* stream);
+DH_API int dh_decoder_state_size(const dh_decoder* h, size_t* bytes);
+DH_API int dh_decoder_state_export(dh_decoder* h, void* h_buf, size_t cap, size_t* written, void* stream);
+DH_API int dh_decoder_state_import(dh_decoder* h, const void* h_buf, size_t bytes, void* stream);
+DH_API int dh_pipe_state_size(const dh_pipe* h, size_t* bytes);
+DH_API int dh_pipe_state_export(dh_pipe* h, void* h_buf, size_t cap, size_t* written, void* stream);
+DH_API int dh_pipe_state_import(dh_pipe* h, const void* h_buf, size_t bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
  * One pipe sharded over the GPUs of a node: one process (rank) per GPU, channels split into contiguous ranges
  * (rank r of R owns [r*N/R, (r+1)*N/R), the first N % R ranks one channel more).  In the reference the same
  * partitioning is "one shell pipe per channel" (examples/dmr-decoder.sh:12-23): channels never interact, so the only

@@ -308,26 +308,37 @@ namespace Digiham {
                 // like the reference, the serializer is never freed (src/pocsag_decoder/pocsag_decoder.cpp:6-8)
                 explicit Decoder(Serializer* serializer): Digiham::Decoder(DH_PROTO_POCSAG, false), serializer(serializer) {}
             protected:
-                // The bank renders `address:N;message:TEXT\n` (StringSerializer).  For another serializer the
-                // lines are split back into {address, message} and re-rendered.
+                // The bank renders `address:N;message:TEXT\n` (StringSerializer) on the device.  For another
+                // serializer the rendered text is dropped and the structured {address, message} records the bank
+                // keeps beside it (dh_decoder_meta_kv) are serialised instead — no re-parsing of the text, so message
+                // bodies with ';', ':' or newlines survive (reference src/pocsag_decoder/message.cpp:16-24).
                 void handleOutput(const uint8_t* data, size_t len) override {
                     if (dynamic_cast<StringSerializer*>(serializer) != nullptr) {
                         pending.append(data, len);
                         return;
                     }
-                    const std::string text((const char*) data, len);
+                    const uint8_t* p = nullptr;
+                    size_t n = 0;
+                    B200::require(dh_decoder_meta_kv(bank, 0, &p, &n), "pocsag records");
                     size_t pos = 0;
-                    while (pos < text.size()) {
-                        size_t next = text.find("\naddress:", pos);
-                        const size_t end = next == std::string::npos ? text.size() - 1 : next;
-                        const std::string line = text.substr(pos, end - pos);
-                        const size_t sep = line.find(";message:");
-                        if (line.compare(0, 8, "address:") == 0 && sep != std::string::npos) {
-                            const std::string out = serializer->serializeMetaData(
-                                {{"address", line.substr(8, sep - 8)}, {"message", line.substr(sep + 9)}});
-                            pending.append((const unsigned char*) out.data(), out.size());
+                    auto get16 = [&]() -> size_t {
+                        const size_t v = p[pos] | (size_t) p[pos + 1] << 8;
+                        pos += 2;
+                        return v;
+                    };
+                    while (pos + 2 <= n) {
+                        std::map<std::string, std::string> record;
+                        const size_t pairs = get16();
+                        for (size_t i = 0; i < pairs; i++) {
+                            const size_t kl = get16();
+                            std::string key((const char*) p + pos, kl);
+                            pos += kl;
+                            const size_t vl = get16();
+                            record[key] = std::string((const char*) p + pos, vl);
+                            pos += vl;
                         }
-                        pos = end + 1;
+                        const std::string out = serializer->serializeMetaData(record);
+                        pending.append((const unsigned char*) out.data(), out.size());
                     }
                 }
                 Serializer* serializer;

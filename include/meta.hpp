@@ -1,9 +1,9 @@
 // meta.hpp — metadata writer surface of the B200 drop-in modules.
 //
-// API-compatible with the public part of the reference's include/meta.hpp:10-47 (Serializer, StringSerializer,
-// MetaWriter, FileMetaWriter, PipelineMetaWriter), implemented header-only.  The reference's MetaCollector
-// (include/meta.hpp:50-66) has no counterpart here: collecting/dirty tracking happens inside libdigiham_b200
-// (device events + host replay), the decoders hand finished key/value maps to the MetaWriter.
+// API-compatible with the reference's include/meta.hpp:10-66 (Serializer, StringSerializer, MetaWriter,
+// FileMetaWriter, PipelineMetaWriter, MetaCollector), implemented header-only.  The B200 decoders do their own
+// collecting / dirty tracking inside libdigiham_b200 (device events + host replay) and hand finished key/value maps
+// to the MetaWriter; MetaCollector is kept for code that derives its own collectors from it.
 #pragma once
 
 #include <csdr/source.hpp>
@@ -81,6 +81,46 @@ namespace Digiham {
                 std::memcpy(writer->getWritePointer(), text.data(), text.size());
                 writer->advance(text.size());
             }
+    };
+
+    // Base of the per-protocol collectors (reference include/meta.hpp:50-66, src/lib/meta.cpp:58-100): subclasses
+    // call sendMetaData() whenever a field changed; between hold() and the matching release() updates are coalesced
+    // into one (the collector is only marked dirty) and sent when the last hold is released.  Owns its writer.
+    class MetaCollector {
+        public:
+            MetaCollector(): MetaCollector(nullptr) {}
+            explicit MetaCollector(MetaWriter* w): writer(w) {}
+            virtual ~MetaCollector() { delete writer; }
+            void setWriter(MetaWriter* w) {
+                delete writer;
+                writer = w;
+            }
+            void hold() { held++; }
+            void release() {
+                if (--held != 0) return;
+                const bool pending = dirty;
+                dirty = false;
+                if (pending) sendMetaData();
+            }
+        protected:
+            virtual std::string getProtocol() = 0;
+            virtual std::map<std::string, std::string> collect() {
+                std::map<std::string, std::string> fields;
+                fields["protocol"] = getProtocol();
+                return fields;
+            }
+            virtual void sendMetaData() {
+                if (writer == nullptr) return;
+                if (held) dirty = true;
+                else sendMetaData(collect());
+            }
+            virtual void sendMetaData(std::map<std::string, std::string> metadata) {
+                if (writer != nullptr) writer->sendMetaData(std::move(metadata));
+            }
+        private:
+            int held = 0;
+            bool dirty = false;
+            MetaWriter* writer;
     };
 
 }

@@ -60,6 +60,17 @@ bool feed(Csdr::Ringbuffer<T>* rb, const std::vector<T>& data, size_t& pos) {
     return true;
 }
 
+// a serializer whose output does not depend on separators inside the values: key=<len>:<value> per field, then 0x1e
+class LengthPrefixedSerializer: public Digiham::Serializer {
+    public:
+        std::string serializeMetaData(std::map<std::string, std::string> metadata) override {
+            std::string out;
+            for (const auto& kv : metadata) out += kv.first + "=" + std::to_string(kv.second.size()) + ":" + kv.second;
+            out += '\x1e';
+            return out;
+        }
+};
+
 int main(int argc, char** argv) {
     if (argc < 4) return 2;
     const std::string proto = argv[1], prefix = argv[3];
@@ -93,10 +104,13 @@ int main(int argc, char** argv) {
         Csdr::Module<float, float>* rrc = nullptr;
         Csdr::Module<float, unsigned char>* demod;
         Digiham::Decoder* dec;
-        if (proto == "pocsag") {
+        if (proto == "pocsag" || proto == "pocsag_custom") {
             demod = new Digiham::Fsk::FskDemodulator(40, true);
             demod->setReader(new Csdr::RingbufferReader<float>(&in));
-            dec = new Digiham::Pocsag::Decoder();
+            // reference include/pocsag_decoder.hpp:12: Decoder(Serializer*) — a caller-supplied serializer receives
+            // the structured {address, message} map of every message
+            if (proto == "pocsag_custom") dec = new Digiham::Pocsag::Decoder(new LengthPrefixedSerializer());
+            else dec = new Digiham::Pocsag::Decoder();
         } else if (proto == "dstar") {
             // examples/dstar-decoder.sh:19-21
             demod = new Digiham::Fsk::FskDemodulator(10);

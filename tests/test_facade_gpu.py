@@ -85,6 +85,24 @@ def test_facade_pocsag_pipe(harness):
     assert b"message:HELLO B200" in out.tobytes()
 
 
+def test_facade_pocsag_custom_serializer_gets_structured_records(harness):
+    """Pocsag::Decoder(Serializer*) (reference include/pocsag_decoder.hpp:12, src/pocsag_decoder/message.cpp:16-24):
+    a caller-supplied serializer sees the {address, message} map itself — message bodies that contain the text
+    separators of the default rendering (';message:', a newline followed by 'address:') arrive intact."""
+    tricky = ["PLAIN", "A;message:B", "X\naddress:7;message:Y", "tail:;\n"]
+    msgs = [(1000 + 8 * k, 3, t) for k, t in enumerate(tricky)]
+    bits = synth.pocsag_bits(msgs, seed=5, lead_in=0)
+    x = synth.modulate(bits, sps=40, levels=synth.LEVELS2[::-1].copy(), snr_db=25, rng=np.random.default_rng(3))
+    out, _ = _run(harness, "pocsag_custom", x)
+    want = b"".join(("address=%d:%d" % (len(str(a)), a)).encode() + ("message=%d:" % len(t)).encode() + t.encode() + b"\x1e"
+                    for a, _, t in msgs)
+    assert out.tobytes() == want
+    # the default serializer on the same signal still equals the reference byte for byte
+    out, _ = _run(harness, "pocsag", x)
+    _, ref_out, _ = oracle_lib.best().pipe(oracle_lib.PROTO_POCSAG, x, chunk=128)
+    assert np.array_equal(out, ref_out)
+
+
 def test_facade_rrc_and_dvf(harness):
     rng = np.random.default_rng(4)
     x = rng.uniform(-1, 1, 5000).astype(np.float32)

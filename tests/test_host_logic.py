@@ -343,3 +343,18 @@ def test_synthetic_generators_are_deterministic():
         for d in range(1 << min(n, 6)):
             cw = synth.encode_block(code, d)
             assert cw >> (synth._P[code][0] - synth._P[code][1]) == d
+
+
+def test_meta_collector_hold_release_semantics():
+    """Digiham::MetaCollector of include/meta.hpp behaves like the reference's (include/meta.hpp:50-66,
+    src/lib/meta.cpp:58-100): updates without a writer are dropped, hold()/release() coalesce updates into one that
+    carries the latest state, the explicit-map overload is not held back, the collector owns (and closes) its writer."""
+    with tempfile.TemporaryDirectory() as d:
+        exe = os.path.join(d, "mc")
+        subprocess.run(["g++", "-std=c++17", "-Wall", "-Werror", "-O1", "-I" + os.path.join(ROOT, "include"),
+                        "-I" + os.path.join(ROOT, "oracle", "csdr_shim"),
+                        os.path.join(ROOT, "tests", "cpp", "meta_collector.cpp"), "-o", exe], check=True)
+        out = os.path.join(d, "meta.txt")
+        subprocess.run([exe, out], check=True)
+        text = open(out).read()
+    assert text == ("call:DL1ABC;protocol:PROBE\n" "x:1\n" "call:DL3GHI;protocol:PROBE\n" "call:DL4JKL;protocol:PROBE\n")

@@ -12,8 +12,9 @@ Everything here is derived from first principles, not copied from the reference'
   matrix is H = [P^T | I]; the syndrome has H's row 0 as its MSB (reference hamming_13_9.c:53-72 and siblings).
   The correction LUT is built by enumerating every error pattern of weight <= t in the same order as the
   reference's *_syndrome_generator.c programs and keeping the FIRST pattern seen per syndrome, which is what
-  the reference's linear search over `corrections[]` returns.  tests/test_fec.py proves equality with the
-  compiled reference for every syndrome.
+  the reference's linear search over `corrections[]` returns.  tests/test_oracle_cpu.py proves LUT equality with
+  the compiled reference for every syndrome on the CPU; tests/test_fec_gpu.py drives the device decoders that use
+  the tables over all words / error patterns.
 """
 import os
 import sys
