@@ -184,8 +184,9 @@ __device__ __forceinline__ int processable(int T, int P, int vo, int sps) {
 __host__ __device__ constexpr int eval_lo(int sps) { return (2 * sps + 3) / 6; }   // == roundf(sps / 3.0f) for 10, 20, 40 (checked by the host)
 __host__ __device__ constexpr int eval_hi(int sps) { return (4 * sps + 3) / 6; }   // == roundf(sps * 2 / 3.0f)
 
-template <int G, int SPS, int THREADS>
-__global__ void __launch_bounds__(THREADS) demod_kernel(const __grid_constant__ DemodParams p) {
+// MINB: minimum resident CTAs per SM the register allocation must allow (caps the registers per thread)
+template <int G, int SPS, int THREADS, int MINB = 0>
+__global__ void __launch_bounds__(THREADS, MINB) demod_kernel(const __grid_constant__ DemodParams p) {
     extern __shared__ __align__(16) float smem[];
     constexpr int kPerWarp = Group<G>::kPerWarp;
     constexpr int CH = Group<G>::kChunk;
@@ -651,6 +652,13 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     const int groups = (threads / 32) * (32 / G);
     const unsigned grid = (h->channels + groups - 1) / groups;
     const size_t smem = (size_t) groups * p.group_floats * sizeof(float);
+#define DH_LAUNCH_DEMOD4(GG, SS, TT, MB)                                                                             \
+    do {                                                                                                             \
+        if (!h->smem_attr_set)                                                                                       \
+            DH_CUDA(cudaFuncSetAttribute(demod_kernel<GG, SS, TT, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                         (int) smem));                                                               \
+        demod_kernel<GG, SS, TT, MB><<<grid, TT, smem, st>>>(p);                                                      \
+    } while (0)
 #define DH_LAUNCH_DEMOD(GG, SS, TT)                                                                                  \
     do {                                                                                                             \
         if (!h->smem_attr_set)                                                                                       \
@@ -658,7 +666,14 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
                                          (int) smem));                                                               \
         demod_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                          \
     } while (0)
-    if (G == 10 && h->sps == 10) {
+    static const int minb = getenv("DH_DEMOD_MINB") ? atoi(getenv("DH_DEMOD_MINB")) : 0;   // experiment switch
+    if (G == 10 && h->sps == 10 && minb == 10) {
+        DH_LAUNCH_DEMOD4(10, 10, kThreads, 10);
+    } else if (G == 10 && h->sps == 10 && minb == 12) {
+        DH_LAUNCH_DEMOD4(10, 10, kThreads, 12);
+    } else if (G == 10 && h->sps == 10 && minb == 16) {
+        DH_LAUNCH_DEMOD4(10, 10, kThreads, 16);
+    } else if (G == 10 && h->sps == 10) {
         DH_LAUNCH_DEMOD(10, 10, kThreads);
     } else if (G == 10 && h->sps == 20) {
         DH_LAUNCH_DEMOD(10, 20, kThreads);
@@ -675,6 +690,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         DH_LAUNCH_DEMOD(32, 0, kThreads);
     }
 #undef DH_LAUNCH_DEMOD
+#undef DH_LAUNCH_DEMOD4
     DH_CUDA(cudaGetLastError());
     h->smem_attr_set = true;
     h->cur ^= 1;   // the carried tails now sit in the other buffer

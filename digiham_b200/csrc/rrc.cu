@@ -9,7 +9,7 @@
 // 2^32 float inputs, that fl32(fl64(s) * fl64(1/g)) == fl32(fl64(s) / g) for g in {8.337797030, 16.67711971}.
 //
 // Kernel shape (1-D convolution, FP32-issue bound at 2*(nZeros+1) flop per sample — no tensor cores):
-//   * one CTA = one (channel, time tile) of TILE = 128 threads x R outputs; R is odd (13..19, chosen per call so
+//   * one CTA = one (channel, time tile) of TILE = 128 threads x R outputs; R is odd (13..25, chosen per call so
 //     that the stream splits into equal tiles) so that the per-thread windows (stride R floats) fall into 32
 //     different shared-memory banks without any padding;
 //   * the tile and its nZeros-sample halo are brought in by TMA 1-D bulk copies (cp.async.bulk -> UBLKCP) that
@@ -32,12 +32,13 @@ namespace {
 
 constexpr int kThreads = 128;
 constexpr int kRDefault = 17;         // outputs per thread; odd, see the kernel comment
-constexpr int kMaxTile = kThreads * 19;
+constexpr int kMaxR = 25;
+constexpr int kMaxTile = kThreads * kMaxR;
 constexpr int kMaxZeros = 1024;
 constexpr int kMaxTapsParam = 164;    // taps that travel in the kernel parameter (constant bank 0)
 // The parameter copy is laid out in groups of R taps padded to a multiple of 4 floats, so that the rolled loop
 // fetches the taps of one group with 16-byte uniform loads (LDCU.128) instead of one LDCU per tap.
-constexpr int kTapSlots = 224;        // >= groups * pad4(R) for 164 taps at R = 13
+constexpr int kTapSlots = 224;        // >= groups * pad4(R) for 164 taps at every R in 13..25
 
 struct alignas(16) TapBlock {
     float c[kTapSlots];
@@ -60,24 +61,27 @@ struct RrcParams {
 };
 
 // Outputs per thread for a call of n samples.  A CTA slot costs the same whether its tile is full or ragged (the
-// surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..19 to
-// minimise tiles * (work per tile): e.g. n = 48000 -> R = 19, 20 tiles instead of 22 + a ragged one at R = 17
-// (R = 15, 25 equal tiles, when the smaller register footprint is preferred: dh_rrc_set_tile_preference).
+// surviving warps of a ragged tile run no faster), so the tile size 128 * R is chosen from odd R in 13..25 to
+// minimise tiles * (work per tile): e.g. n = 48000 -> R = 25, 15 equal tiles of 3200 samples (fewest window loads,
+// tap fetches and prologues per output) instead of 22 + a ragged one at R = 17; R = 15, 25 equal tiles, when the
+// smaller register footprint is preferred (dh_rrc_set_tile_preference).
 inline int pick_r(size_t n, int nz, bool prefer_small) {
     static const int forced = [] {   // tuning switch, read once
         const char* env = getenv("DH_RRC_R");
         const int r = env ? atoi(env) : 0;
-        return (r == 13 || r == 15 || r == 17 || r == 19) ? r : 0;
+        return (r >= 13 && r <= kMaxR && (r & 1)) ? r : 0;
     }();
     if (forced) return forced;
     int best = kRDefault;
     double best_cost = 1e300;
-    for (int r = 19; r >= 13; r -= 2) {
+    // beside other kernels the large tiles (R > 19: 53..63 registers) lose more through their footprint than they gain
+    for (int r = prefer_small ? 19 : kMaxR; r >= 13; r -= 2) {
         const size_t tiles = (n + (size_t) kThreads * r - 1) / ((size_t) kThreads * r);
         // per tile and thread: (nz + 1) * (2 r + 2) issue slots + fixed prologue / epilogue
         double cost = (double) tiles * ((nz + 1) * (2.0 * r + 2.0) + 6.0 * r + 150.0);
         // beside other kernels (dh_pipe_set_async) a smaller register footprint keeps more CTAs resident: measured
-        // 1.331 ms per pipelined DMR step at R = 15 against 1.355 ms at R = 19, although R = 19 is 1 % faster alone
+        // 1.334 ms per pipelined DMR step at R = 15 (40 registers) against 1.352 at R = 19 and 1.370 at R = 25 (63
+        // registers), although R = 25 is 3 % faster alone (0.979 vs 1.008 ms, profiles/r02_sweep_step.txt)
         if (prefer_small) cost *= 1.0 + 0.004 * r;
         if (cost < best_cost * 0.999) {
             best_cost = cost;
@@ -423,6 +427,9 @@ int rrc_launch(dh_rrc* h, const void* d_in, size_t in_pitch, float* d_out, size_
             case 13: DH_LAUNCH_RRC(13); break;
             case 15: DH_LAUNCH_RRC(15); break;
             case 19: DH_LAUNCH_RRC(19); break;
+            case 21: DH_LAUNCH_RRC(21); break;
+            case 23: DH_LAUNCH_RRC(23); break;
+            case 25: DH_LAUNCH_RRC(25); break;
             default: DH_LAUNCH_RRC(17); break;
         }
     }
