@@ -28,6 +28,7 @@ from ._capi import (  # noqa: F401
     FMT_F32,
     FMT_S16,
     SHARD_SCATTER,
+    OPT_DMR_LC_FEC,
 )
 
-__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PinnedBlock", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "PROTO_NXDN", "PROTO_DSTAR", "RRC_WIDE", "RRC_NARROW", "FMT_F32", "FMT_S16", "SHARD_SCATTER"]
+__all__ = ["DhError", "lib", "lib_path", "RrcBank", "DemodBank", "DecoderBank", "Pipe", "DvfBank", "PinnedBlock", "PROTO_DMR", "PROTO_YSF", "PROTO_POCSAG", "PROTO_NXDN", "PROTO_DSTAR", "RRC_WIDE", "RRC_NARROW", "FMT_F32", "FMT_S16", "SHARD_SCATTER", "OPT_DMR_LC_FEC"]

@@ -11,6 +11,7 @@ RRC_WIDE = 0
 RRC_NARROW = 1
 FMT_F32, FMT_S16 = 0, 1
 SHARD_SCATTER = 1
+OPT_DMR_LC_FEC = 1
 PROTO_DMR, PROTO_YSF, PROTO_POCSAG, PROTO_NXDN, PROTO_DSTAR = 0, 1, 2, 3, 4
 
 
@@ -64,6 +65,7 @@ def lib():
     L.dh_decoder_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
     L.dh_decoder_reserve.argtypes = [ctypes.c_void_p, ctypes.c_size_t, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
     L.dh_decoder_set_slot_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint8]
+    L.dh_decoder_set_option.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.dh_decoder_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                      ctypes.c_size_t, ctypes.c_void_p]
     L.dh_decoder_collect.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
@@ -349,6 +351,10 @@ class DecoderBank:
 
     def set_slot_filter(self, filt, channel=-1):
         check(lib().dh_decoder_set_slot_filter(self._h, channel, filt))
+
+    def set_option(self, option, value, channel=-1):
+        """Opt-in modes beyond the reference (dh_decoder_set_option), e.g. OPT_DMR_LC_FEC."""
+        check(lib().dh_decoder_set_option(self._h, channel, option, value))
 
     def process(self, sym, nsym, max_nsym=None, stream=None):
         """sym: uint8 CUDA tensor [channels, >=max_nsym] or (ptr, pitch); nsym: int32 CUDA tensor [channels]."""

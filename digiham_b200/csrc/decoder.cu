@@ -191,8 +191,23 @@ int dh_decoder_reserve(dh_decoder* h, size_t max_syms, uint8_t** d_buf, size_t* 
 int dh_decoder_set_slot_filter(dh_decoder* h, int channel, uint8_t filter) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_set_slot_filter: handle is NULL");
     DH_REQUIRE(channel < (int) h->channels, DH_E_INVALID, "dh_decoder_set_slot_filter: channel out of range");
-    if (channel < 0) std::fill(h->h_slot_filter.begin(), h->h_slot_filter.end(), filter);
-    else h->h_slot_filter[channel] = filter;
+    // the per-channel control byte carries the filter in its low nibble and the decoder options above it
+    auto put = [&](uint8_t& b) { b = (uint8_t) ((b & 0xF0u) | (filter & 0x0Fu)); };
+    if (channel < 0) for (auto& b : h->h_slot_filter) put(b);
+    else put(h->h_slot_filter[channel]);
+    h->filter_dirty = true;
+    return DH_OK;
+}
+
+int dh_decoder_set_option(dh_decoder* h, int channel, int option, int value) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_set_option: handle is NULL");
+    DH_REQUIRE(channel < (int) h->channels, DH_E_INVALID, "dh_decoder_set_option: channel out of range");
+    DH_REQUIRE(option == DH_OPT_DMR_LC_FEC && h->proto == DH_PROTO_DMR, DH_E_UNSUPPORTED,
+               "dh_decoder_set_option: option %d is not available for protocol %d", option, h->proto);
+    DH_REQUIRE(value >= 0 && value <= 2, DH_E_INVALID, "dh_decoder_set_option: value %d out of range", value);
+    auto put = [&](uint8_t& b) { b = (uint8_t) ((b & 0xCFu) | ((unsigned) value << 4)); };
+    if (channel < 0) for (auto& b : h->h_slot_filter) put(b);
+    else put(h->h_slot_filter[channel]);
     h->filter_dirty = true;
     return DH_OK;
 }

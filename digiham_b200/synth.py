@@ -202,7 +202,31 @@ def dmr_voice_burst(slot, rng, sync="bs_voice", emb=None, fragment=None, lcss_ca
     return f
 
 
+def _gf256_mul(a, b):
+    """GF(2^8) with the field polynomial x^8 + x^4 + x^3 + x^2 + 1 (ETSI TS 102 361-1 B.3.6)."""
+    acc = 0
+    for i in range(8):
+        if (b >> i) & 1:
+            acc ^= a << i
+    for i in range(14, 7, -1):
+        if acc & (1 << i):
+            acc ^= 0x11D << (i - 8)
+    return acc
+
+
+def dmr_rs_12_9_parity(lc9, mask=0x96):
+    """The three Reed-Solomon (12,9) parity octets of a 9-octet full LC, generator (x + a)(x + a^2)(x + a^3) =
+    x^3 + 14 x^2 + 56 x + 64, XOR-ed with the data-type mask (0x96 voice LC header, 0x99 terminator with LC)."""
+    reg = [0, 0, 0]                      # remainder, highest degree first
+    for d in lc9:
+        fb = d ^ reg[0]
+        reg = [reg[1] ^ _gf256_mul(fb, 14), reg[2] ^ _gf256_mul(fb, 56), _gf256_mul(fb, 64)]
+    return [r ^ mask for r in reg]
+
+
 def dmr_full_lc(opcode, target, source, fid=0, options=0, rng=None):
+    """9 LC octets + 3 tail octets.  The reference never looks at the tail (src/dmr_decoder/lc.cpp:8-11), so the
+    default generator fills it with random octets; dmr_rs_12_9_parity makes a standard-conforming tail."""
     lc = [opcode & 0x3F, fid, options, (target >> 16) & 0xFF, (target >> 8) & 0xFF, target & 0xFF,
           (source >> 16) & 0xFF, (source >> 8) & 0xFF, source & 0xFF]
     tail = list(rng.integers(0, 256, size=3)) if rng is not None else [0, 0, 0]

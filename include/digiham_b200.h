@@ -180,6 +180,14 @@ DH_API int dh_decoder_reserve(dh_decoder* h, size_t max_syms, uint8_t** d_buf, s
 /* Dmr::Decoder::setSlotFilter (include/dmr_decoder.hpp:12): bit 0 = slot 0, bit 1 = slot 1; channel < 0 = all.
  * Takes effect at the next dh_decoder_process call. */
 DH_API int dh_decoder_set_slot_filter(dh_decoder* h, int channel, uint8_t filter);
+/* Opt-in decoder modes that go BEYOND the reference (every option is off by default, and off means byte-exact
+ * reference behaviour).  channel < 0 = all channels; takes effect at the next dh_decoder_process call.
+ *   DH_OPT_DMR_LC_FEC  the Reed-Solomon (12,9) check of full link control words the reference leaves as a TODO
+ *                      (src/dmr_decoder/lc.cpp:8-11, bptc_196_96.c:44; ETSI TS 102 361-1 B.3.6) on voice LC headers
+ *                      and terminators with LC: 0 = none, 1 = verify (a word that fails is ignored), 2 = verify and
+ *                      correct one octet error.  DH_E_UNSUPPORTED for other protocols. */
+#define DH_OPT_DMR_LC_FEC 1
+DH_API int dh_decoder_set_option(dh_decoder* h, int channel, int option, int value);
 /* Consumes d_nsym[c] (<= max_nsym) new symbols of every channel c (d_nsym is a DEVICE array). */
 DH_API int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, const uint32_t* d_nsym,
                               size_t max_nsym, void* stream);

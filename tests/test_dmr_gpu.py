@@ -110,3 +110,80 @@ def test_dmr_decoder_noise_and_ragged_counts():
         assert bank.output(ch) == ref_out.tobytes(), ch
         assert bank.meta(ch) == ref_meta, ch
     bank.close()
+
+
+# ---- opt-in mode beyond the reference: Reed-Solomon (12,9) on full link control words -----------------------------
+def _lc_script(seed, variant):
+    """Burst descriptors of slot 0 (slot 1 idles): calls of header / two voice superframes / terminator.  Returns
+    (bursts as sent, bursts a decoder WITHOUT the RS check must see to behave like one WITH it)."""
+    rng = np.random.default_rng(seed)
+    sent, equiv_verify, equiv_correct = [], [], []
+    for call in range(6):
+        lc9 = synth.dmr_full_lc(0 if call % 2 else 3, int(rng.integers(1, 1 << 24)), int(rng.integers(1, 1 << 24)))[:9]
+        for data_type, mask in ((synth.DMR_DT_VOICE_LC, 0x96), (synth.DMR_DT_TERMINATOR_LC, 0x99)):
+            good = lc9 + synth.dmr_rs_12_9_parity(lc9, mask)
+            if variant == "valid":
+                tx, v, c = good, ("data", data_type, good), ("data", data_type, good)
+            elif variant == "random":
+                bad = lc9 + [int(t) ^ 0x5A for t in good[9:]]
+                tx, v, c = bad, ("data", synth.DMR_DT_CSBK, bad), ("data", synth.DMR_DT_CSBK, bad)
+            else:   # one octet of the 12 is wrong: detected by "verify", repaired by "correct"
+                pos = int(rng.integers(0, 12))
+                bad = list(good)
+                bad[pos] ^= int(rng.integers(1, 256))
+                tx, v, c = bad, ("data", synth.DMR_DT_CSBK, bad), ("data", data_type, good)
+            if data_type == synth.DMR_DT_VOICE_LC:
+                head = (("data", data_type, tx), v, c)
+            else:
+                tail = (("data", data_type, tx), v, c)
+        voice = [("voice", None, None)] + [("voice", (1, 0, 0), None)] * 5
+        for lst, k in ((sent, 0), (equiv_verify, 1), (equiv_correct, 2)):
+            lst.append(head[k])
+            lst.extend(voice * 2)
+            lst.append(tail[k])
+            lst.extend([("data", synth.DMR_DT_IDLE, [0] * 12)] * 2)
+    return sent, equiv_verify, equiv_correct
+
+
+def _render(script, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    idle = ("data", synth.DMR_DT_IDLE, [0] * 12)
+    for kind, a, b in script:
+        for slot, (k, x, y) in enumerate(((kind, a, b), idle)):
+            out.append(synth.dmr_data_burst(slot, x, y, rng) if k == "data" else synth.dmr_voice_burst(slot, rng, emb=x, fragment=y))
+    return np.concatenate(out).astype(np.uint8)
+
+
+@pytest.mark.parametrize("variant", ["valid", "random", "one_error"])
+def test_dmr_opt_in_rs_12_9_on_full_lc(variant):
+    """DH_OPT_DMR_LC_FEC (off by default: everything above runs with the reference's behaviour).  The reference has
+    no RS check to compare with, so the expectation comes from the reference itself on an EQUIVALENT stream: a full-LC
+    burst the check rejects must act like a burst type the decoder ignores (CSBK), a repaired one like the clean one."""
+    import digiham_b200 as dh
+    sent, eq_verify, eq_correct = _lc_script(7, variant)
+    s_sent, s_verify, s_correct = _render(sent, 99), _render(eq_verify, 99), _render(eq_correct, 99)
+    orc = oracle_lib.best()
+    want = {0: orc.decode(oracle_lib.PROTO_DMR, s_sent), 1: orc.decode(oracle_lib.PROTO_DMR, s_verify),
+            2: orc.decode(oracle_lib.PROTO_DMR, s_correct)}
+    if variant != "valid":
+        assert want[0][1] != want[1][1], "the two streams must differ in metadata for the test to mean anything"
+    got = {}
+    for mode in (0, 1, 2):
+        bank = dh.DecoderBank(2, dh.PROTO_DMR)
+        bank.set_option(dh.OPT_DMR_LC_FEC, mode, channel=0)      # channel 1 keeps the default
+        sym = np.stack([s_sent, s_sent])
+        out, meta = _gpu_decode(bank, sym, [5000, sym.shape[1] - 5000])
+        assert out[0] == want[mode][0].tobytes() and meta[0] == want[mode][1], (variant, mode)
+        assert out[1] == want[0][0].tobytes() and meta[1] == want[0][1], (variant, mode)
+        got[mode] = meta[0]
+        bank.close()
+    assert b"source:" in got[0] and len(want[0][0]) > 27 * 20
+    if variant == "random":
+        assert b"source:" not in got[1] and b"source:" not in got[2]
+    if variant == "one_error":
+        assert got[1] != got[2] and b"source:" in got[2]
+    ysf = dh.DecoderBank(1, dh.PROTO_YSF)
+    with pytest.raises(dh.DhError):
+        ysf.set_option(dh.OPT_DMR_LC_FEC, 1)
+    ysf.close()
