@@ -257,24 +257,30 @@ def sharded_arm(args, dh, dist, dev, rank, world, stream, barrier, max_over_rank
     total = Cs * world
     out = {"channels_per_gpu": Cs, "channels_total": total, "samples_per_channel_per_step": L}
     check_per_rank = 64
+    # rank 0 holds two different steps' blocks of ALL channels (per-rank seeds differ, so a misplaced shard would
+    # show); the int16 blocks are the float32 ones quantised like an rtl_fm discriminator output
+    pitch32 = (L + 3) & ~3
+    pitch16 = (L + 7) & ~7
+    blocks32 = blocks16 = ref32 = ref16 = None
+    if rank == 0:
+        blocks32 = [torch.zeros((total, pitch32), dtype=torch.float32, device=dev) for _ in range(2)]
+        blocks16 = [torch.zeros((total, pitch16), dtype=torch.int16, device=dev) for _ in range(2)]
+        ref32, ref16 = [], []
+        for r in range(world):
+            xr = synth.dmr_channel_bank(Cs, 2 * L, seed=777 + r, device=dev)[0][:, :2 * L]
+            xs = torch.clamp(torch.round(xr * 20000.0), -32768, 32767).to(torch.int16)
+            for k in range(2):
+                blocks32[k][r * Cs:(r + 1) * Cs, :L] = xr[:, k * L:(k + 1) * L]
+                blocks16[k][r * Cs:(r + 1) * Cs, :L] = xs[:, k * L:(k + 1) * L]
+            ref32.append(xr[:check_per_rank].cpu().numpy())
+            ref16.append(xs[:check_per_rank].cpu().numpy().astype(np.float32) / np.float32(32767))
+            del xr, xs
     for fmt_name, fmt, dtype in (("f32", dh.FMT_F32, torch.float32), ("s16", dh.FMT_S16, torch.int16)):
         sp = shard.ShardedPipe(total, dh.PROTO_DMR, max_chunk=L, device=dev, fmt=fmt)
         pitch = sp.pitch
-        blocks = None
-        ref_rows = None
-        if rank == 0:
-            # two different steps' blocks for all channels (per-rank seeds differ, so a misplaced shard would show)
-            blocks = [torch.zeros((total, pitch), dtype=dtype, device=dev) for _ in range(2)]
-            ref_rows = []
-            for r in range(world):
-                xr = synth.dmr_channel_bank(Cs, 2 * L, seed=777 + r, device=dev)[0][:, :2 * L]
-                if fmt == dh.FMT_S16:
-                    xr = torch.clamp(torch.round(xr * 20000.0), -32768, 32767).to(torch.int16)
-                for k in range(2):
-                    blocks[k][r * Cs:(r + 1) * Cs, :L] = xr[:, k * L:(k + 1) * L]
-                head = xr[:check_per_rank].cpu().numpy()
-                ref_rows.append(head.astype(np.float32) / np.float32(32767) if fmt == dh.FMT_S16 else head)
-                del xr
+        blocks = blocks16 if fmt == dh.FMT_S16 else blocks32
+        ref_rows = ref16 if fmt == dh.FMT_S16 else ref32
+        assert pitch == (pitch16 if fmt == dh.FMT_S16 else pitch32)
         # parity first, on the fresh streams: two steps through scatter / kernels / gather / read-back, then the
         # gathered frames + metadata of the first `check_per_rank` channels of EVERY rank against the reference
         sp.submit(blocks[0] if rank == 0 else None, L, scatter=True)
@@ -346,8 +352,8 @@ def sharded_arm(args, dh, dist, dev, rank, world, stream, barrier, max_over_rank
         out["parity" + key] = parity
         out["gather_wire_bytes_per_rank_per_step"] = wire_bytes
         sp.close()
-        del blocks
-        torch.cuda.empty_cache()
+    del blocks32, blocks16
+    torch.cuda.empty_cache()
     out["unit"] = "Msamples/s"
     out["note"] = ("dh_shard_*: rank 0 holds every channel's block in HBM; per step NCCL scatter (grouped send/recv) -> "
                    "K1/K2/K3 on each rank -> pack -> NCCL gather to rank 0, consecutive steps overlapped on three streams "

@@ -130,6 +130,16 @@ struct ResultSink {
     // (synchronises it), appends the bytes and replays the events in order.  The flag words are OR-ed into *flags.
     int ingest(const uint32_t* d_counts, const uint8_t* d_out, size_t out_pitch, const DecEvent* d_ev, size_t ev_pitch,
                uint32_t n, uint32_t c0, cudaStream_t st, uint32_t* flags);
+    // Several blocks at once (the gathering rank of a sharded pipe: one block per rank): all counts are fetched
+    // with one synchronisation, all rows with a second one, then every channel is replayed in one parallel pass.
+    struct Block {
+        const uint32_t* d_counts;
+        const uint8_t* d_out;
+        const DecEvent* d_ev;
+        uint32_t n;    // channels of the block
+        uint32_t c0;   // first sink channel
+    };
+    int ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch, size_t ev_pitch, cudaStream_t st, uint32_t* flags);
     void clear();
     void release();
 };

@@ -43,68 +43,122 @@ int ResultSink::init(int proto, uint32_t nchannels) {
 
 int ResultSink::ingest(const uint32_t* d_counts, const uint8_t* d_out, size_t out_pitch, const DecEvent* d_ev,
                        size_t ev_pitch, uint32_t n, uint32_t c0, cudaStream_t st, uint32_t* flags_out) {
-    DH_REQUIRE((size_t) c0 + n <= channels, DH_E_INVALID, "result sink: channel range out of bounds");
-    if (n == 0) return DH_OK;
-    DH_CUDA(cudaMemcpyAsync(h_counts, d_counts, 3 * (size_t) n * sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    const Block b = {d_counts, d_out, d_ev, n, c0};
+    return ingest_blocks(&b, 1, out_pitch, ev_pitch, st, flags_out);
+}
+
+int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch, size_t ev_pitch, cudaStream_t st,
+                              uint32_t* flags_out) {
+    struct Plan {
+        size_t counts_off;   // into h_counts (uint32 units)
+        size_t out_off;      // into h_out (bytes)
+        size_t ev_off;       // into h_ev (records)
+        uint32_t max_out, max_ev;
+    };
+    std::vector<Plan> plan((size_t) nblocks);
+    size_t total = 0;
+    for (int b = 0; b < nblocks; b++) {
+        DH_REQUIRE((size_t) blocks[b].c0 + blocks[b].n <= channels, DH_E_INVALID, "result sink: channel range out of bounds");
+        plan[b].counts_off = 3 * total;
+        total += blocks[b].n;
+    }
+    DH_REQUIRE(total <= channels, DH_E_INVALID, "result sink: more channels than the sink holds");
+    if (total == 0) return DH_OK;
+    // pass 1: the per-channel counts of every block
+    for (int b = 0; b < nblocks; b++) {
+        if (blocks[b].n == 0) continue;
+        DH_CUDA(cudaMemcpyAsync(h_counts + plan[b].counts_off, blocks[b].d_counts, 3 * (size_t) blocks[b].n * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, st));
+    }
     DH_CUDA(cudaStreamSynchronize(st));
-    total_d2h += 3 * (uint64_t) n * sizeof(uint32_t);
-    const uint32_t* out_len = h_counts;
-    const uint32_t* ev_len = h_counts + n;
-    const uint32_t* flags = h_counts + 2 * (size_t) n;
-    uint32_t max_out = 0, max_ev = 0, any_flags = 0;
-    for (uint32_t c = 0; c < n; c++) {
-        max_out = std::max(max_out, out_len[c]);
-        max_ev = std::max(max_ev, ev_len[c]);
-        any_flags |= flags[c];
+    total_d2h += 3 * (uint64_t) total * sizeof(uint32_t);
+    uint32_t any_flags = 0;
+    size_t out_bytes = 0, ev_records = 0;
+    for (int b = 0; b < nblocks; b++) {
+        const uint32_t n = blocks[b].n;
+        const uint32_t* out_len = h_counts + plan[b].counts_off;
+        const uint32_t* ev_len = out_len + n;
+        const uint32_t* flags = out_len + 2 * (size_t) n;
+        uint32_t max_out = 0, max_ev = 0;
+        for (uint32_t c = 0; c < n; c++) {
+            max_out = std::max(max_out, out_len[c]);
+            max_ev = std::max(max_ev, ev_len[c]);
+            any_flags |= flags[c];
+        }
+        DH_REQUIRE(max_out <= out_pitch && max_ev <= ev_pitch, DH_E_STATE,
+                   "result sink: device counts exceed the slot widths (%u > %zu or %u > %zu)", max_out, out_pitch, max_ev,
+                   ev_pitch);
+        plan[b].max_out = max_out;
+        plan[b].max_ev = max_ev;
+        plan[b].out_off = out_bytes;
+        plan[b].ev_off = ev_records;
+        out_bytes += (size_t) n * max_out;
+        ev_records += (size_t) n * max_ev;
     }
     if (flags_out) *flags_out |= any_flags;
-    DH_REQUIRE(max_out <= out_pitch && max_ev <= ev_pitch, DH_E_STATE,
-               "result sink: device counts exceed the slot widths (%u > %zu or %u > %zu)", max_out, out_pitch, max_ev,
-               ev_pitch);
-    if (max_out) {
-        int rc = grow_pinned((void**) &h_out, &h_out_bytes, (size_t) n * max_out);
-        if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h_out, max_out, d_out, out_pitch, max_out, n, cudaMemcpyDeviceToHost, st));
-        total_d2h += (uint64_t) n * max_out;
-    }
-    if (max_ev) {
-        const size_t w = (size_t) max_ev * sizeof(DecEvent);
-        int rc = grow_pinned((void**) &h_ev, &h_ev_bytes, (size_t) n * w);
-        if (rc != DH_OK) return rc;
-        DH_CUDA(cudaMemcpy2DAsync(h_ev, w, d_ev, ev_pitch * sizeof(DecEvent), w, n, cudaMemcpyDeviceToHost, st));
-        total_d2h += (uint64_t) n * w;
+    // pass 2: the used widths of the byte rows and event rows of every block
+    int rc = grow_pinned((void**) &h_out, &h_out_bytes, out_bytes);
+    if (rc == DH_OK) rc = grow_pinned((void**) &h_ev, &h_ev_bytes, ev_records * sizeof(DecEvent));
+    if (rc != DH_OK) return rc;
+    for (int b = 0; b < nblocks; b++) {
+        const uint32_t n = blocks[b].n;
+        if (plan[b].max_out) {
+            DH_CUDA(cudaMemcpy2DAsync(h_out + plan[b].out_off, plan[b].max_out, blocks[b].d_out, out_pitch, plan[b].max_out, n,
+                                      cudaMemcpyDeviceToHost, st));
+        }
+        if (plan[b].max_ev) {
+            const size_t w = (size_t) plan[b].max_ev * sizeof(DecEvent);
+            DH_CUDA(cudaMemcpy2DAsync(h_ev + plan[b].ev_off, w, blocks[b].d_ev, ev_pitch * sizeof(DecEvent), w, n,
+                                      cudaMemcpyDeviceToHost, st));
+        }
     }
     DH_CUDA(cudaStreamSynchronize(st));
-    // per-channel appends and metadata replay are independent: spread them over a few host threads
-    auto work = [&](uint32_t a, uint32_t b, uint64_t* sums) {
-        for (uint32_t c = a; c < b; c++) {
-            ChannelResult& r = results[c0 + c];
+    total_d2h += out_bytes + ev_records * sizeof(DecEvent);
+    // pass 3: per-channel appends and metadata replay are independent: one parallel pass over all blocks
+    auto work = [&](int b, uint32_t c_lo, uint32_t c_hi, uint64_t* sums) {
+        const uint32_t n = blocks[b].n;
+        const uint32_t* out_len = h_counts + plan[b].counts_off;
+        const uint32_t* ev_len = out_len + n;
+        const uint32_t max_out = plan[b].max_out, max_ev = plan[b].max_ev;
+        for (uint32_t c = c_lo; c < c_hi; c++) {
+            ChannelResult& r = results[blocks[b].c0 + c];
+            const uint8_t* bytes = h_out + plan[b].out_off + (size_t) c * max_out;
             if (out_len[c]) {
-                r.bytes.append(reinterpret_cast<const char*>(h_out + (size_t) c * max_out), out_len[c]);
+                r.bytes.append(reinterpret_cast<const char*>(bytes), out_len[c]);
                 sums[0] += out_len[c];
             }
             sums[2] += ev_len[c];
-            MetaReplay* rp = replay[c0 + c];
+            MetaReplay* rp = replay[blocks[b].c0 + c];
             if (ev_len[c] && rp) {
                 const size_t before = r.meta.size();
                 rp->kv_sink = &r.meta_kv;
-                rp->apply_with_output(h_ev + (size_t) c * max_ev, ev_len[c], h_out + (size_t) c * max_out, out_len[c], r.meta);
+                rp->apply_with_output(h_ev + plan[b].ev_off + (size_t) c * max_ev, ev_len[c], bytes, out_len[c], r.meta);
                 sums[1] += r.meta.size() - before;
             }
         }
     };
-    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 8u);
-    if (n < 256) nthreads = 1;
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), total >= 16384 ? 24u : 8u);
+    if (total < 256) nthreads = 1;
     std::vector<uint64_t> sums((size_t) nthreads * 8, 0);   // 8 slots apart: no false sharing
+    // thread t takes the t-th slice of the concatenated channel list
+    auto run = [&](unsigned t) {
+        const size_t per = (total + nthreads - 1) / nthreads;
+        size_t lo = std::min(total, (size_t) t * per), hi = std::min(total, (size_t) (t + 1) * per), base = 0;
+        for (int b = 0; b < nblocks && lo < hi; b++) {
+            const size_t n = blocks[b].n;
+            if (lo < base + n) {
+                const size_t a = lo - base, e = std::min(n, hi - base);
+                work(b, (uint32_t) a, (uint32_t) e, sums.data() + (size_t) t * 8);
+                lo = base + e;
+            }
+            base += n;
+        }
+    };
     if (nthreads == 1) {
-        work(0, n, sums.data());
+        run(0);
     } else {
         std::vector<std::thread> pool;
-        const uint32_t per = (n + nthreads - 1) / nthreads;
-        for (unsigned t = 0; t < nthreads; t++) {
-            const uint32_t a = std::min(n, t * per), b = std::min(n, (t + 1) * per);
-            pool.emplace_back(work, a, b, sums.data() + (size_t) t * 8);
-        }
+        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(run, t);
         for (auto& t : pool) t.join();
     }
     for (unsigned t = 0; t < nthreads; t++) {

@@ -459,14 +459,15 @@ int dh_shard_collect_step(dh_shard* h) {
     h->collected++;
     if (h->rank != h->root) return DH_OK;
     uint32_t flags = 0;
+    std::vector<dh::ResultSink::Block> blocks((size_t) h->world);
     for (int r = 0; r < h->world; r++) {
         const uint32_t n = h->n_of[r];
         const uint8_t* region = h->d_wire[slot] + h->region_off[r];
-        int rc = h->sink.ingest(reinterpret_cast<const uint32_t*>(region), region + h->wire.off_out(n), h->wire.w_out,
-                                reinterpret_cast<const dh::DecEvent*>(region + h->wire.off_ev(n)), h->wire.w_ev, n,
-                                (uint32_t) h->lo_of[r], h->s_back, &flags);
-        if (rc != DH_OK) return rc;
+        blocks[r] = {reinterpret_cast<const uint32_t*>(region), region + h->wire.off_out(n),
+                     reinterpret_cast<const dh::DecEvent*>(region + h->wire.off_ev(n)), n, (uint32_t) h->lo_of[r]};
     }
+    int rc = h->sink.ingest_blocks(blocks.data(), h->world, h->wire.w_out, h->wire.w_ev, h->s_back, &flags);
+    if (rc != DH_OK) return rc;
     DH_REQUIRE(flags == 0, DH_E_STATE, "dh_shard_collect_step: result slots overflowed on some rank (flags 0x%x)", flags);
     return DH_OK;
 }
