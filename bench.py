@@ -139,19 +139,21 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             try:
                 sm.append(float(r[1]))
                 smax.append(float(r[2]))
+                power.append(float(r[3]))
                 for k, nme in enumerate(names):
                     if r[5 + k].lower().startswith("active"):
                         reasons.add(nme)
             except Exception:
                 continue
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "sm_mhz_min": min(sm) if sm else None, "power_w_median": statistics.median(power) if power else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def proto_ids(name):

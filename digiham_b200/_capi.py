@@ -65,6 +65,7 @@ def lib():
     L.dh_decoder_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
     L.dh_decoder_reserve.argtypes = [ctypes.c_void_p, ctypes.c_size_t, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
     L.dh_decoder_set_slot_filter.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint8]
+    L.dh_decoder_set_meta_kv.argtypes = [ctypes.c_void_p, ctypes.c_int]
     L.dh_decoder_set_option.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int]
     L.dh_decoder_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
                                      ctypes.c_size_t, ctypes.c_void_p]

@@ -289,6 +289,12 @@ int dh_decoder_meta_kv(dh_decoder* h, uint32_t channel, const uint8_t** data, si
     return DH_OK;
 }
 
+int dh_decoder_set_meta_kv(dh_decoder* h, int enable) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_set_meta_kv: handle is NULL");
+    h->sink.want_kv = enable != 0;
+    return DH_OK;
+}
+
 int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_totals: handle is NULL");
     if (out_bytes) *out_bytes = h->sink.total_bytes;

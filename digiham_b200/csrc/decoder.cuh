@@ -123,6 +123,9 @@ struct ResultSink {
     DecEvent* h_ev = nullptr;
     size_t h_ev_bytes = 0;
     uint64_t total_bytes = 0, total_meta = 0, total_events = 0, total_d2h = 0;
+    // key/value records beside the text lines (dh_decoder_meta_kv): kept for small banks (the facade's one-channel
+    // banks apply their own Serializer to them), off for large ones unless asked for (dh_decoder_set_meta_kv)
+    bool want_kv = false;
 
     int init(int proto, uint32_t nchannels);
     // Reads one device result block — counts [3][n] (out_len, ev_len, flags), byte rows [n][out_pitch], event rows

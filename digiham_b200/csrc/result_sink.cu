@@ -8,6 +8,8 @@
 #include "decoder_ops.hpp"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <thread>
 #include <vector>
 
@@ -32,6 +34,7 @@ int ResultSink::init(int proto, uint32_t nchannels) {
     const ProtoOps* ops = proto_ops(proto);
     DH_REQUIRE(ops != nullptr, DH_E_UNSUPPORTED, "result sink: protocol %d not supported", proto);
     channels = nchannels;
+    want_kv = nchannels <= 64;
     results.resize(nchannels);
     replay.assign(nchannels, nullptr);
     if (ops->make_replay) {
@@ -64,6 +67,8 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
     }
     DH_REQUIRE(total <= channels, DH_E_INVALID, "result sink: more channels than the sink holds");
     if (total == 0) return DH_OK;
+    static const bool timing = getenv("DH_SINK_TIMING") != nullptr;   // diagnostics: pass times on stderr
+    const auto t0 = std::chrono::steady_clock::now();
     // pass 1: the per-channel counts of every block
     for (int b = 0; b < nblocks; b++) {
         if (blocks[b].n == 0) continue;
@@ -113,6 +118,7 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
         }
     }
     DH_CUDA(cudaStreamSynchronize(st));
+    const auto t1 = std::chrono::steady_clock::now();
     total_d2h += out_bytes + ev_records * sizeof(DecEvent);
     // pass 3: per-channel appends and metadata replay are independent: one parallel pass over all blocks
     auto work = [&](int b, uint32_t c_lo, uint32_t c_hi, uint64_t* sums) {
@@ -131,7 +137,7 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
             MetaReplay* rp = replay[blocks[b].c0 + c];
             if (ev_len[c] && rp) {
                 const size_t before = r.meta.size();
-                rp->kv_sink = &r.meta_kv;
+                rp->kv_sink = want_kv ? &r.meta_kv : nullptr;
                 rp->apply_with_output(h_ev + plan[b].ev_off + (size_t) c * max_ev, ev_len[c], bytes, out_len[c], r.meta);
                 sums[1] += r.meta.size() - before;
             }
@@ -161,10 +167,20 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
         for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(run, t);
         for (auto& t : pool) t.join();
     }
+    uint64_t ev_now = 0, meta_now = 0;
     for (unsigned t = 0; t < nthreads; t++) {
         total_bytes += sums[(size_t) t * 8];
         total_meta += sums[(size_t) t * 8 + 1];
         total_events += sums[(size_t) t * 8 + 2];
+        meta_now += sums[(size_t) t * 8 + 1];
+        ev_now += sums[(size_t) t * 8 + 2];
+    }
+    if (timing) {
+        const auto t2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sink] %zu channels, %d blocks: copies %.2f ms (%.1f MB), replay %.2f ms on %u threads (%llu events, %llu meta bytes)\n",
+                total, nblocks, std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                (out_bytes + ev_records * sizeof(DecEvent)) / 1e6, std::chrono::duration<double, std::milli>(t2 - t1).count(),
+                nthreads, (unsigned long long) ev_now, (unsigned long long) meta_now);
     }
     return DH_OK;
 }

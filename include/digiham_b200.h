@@ -210,6 +210,9 @@ DH_API int dh_decoder_meta(dh_decoder* h, uint32_t channel, const char** text, s
  * (include/meta.hpp:10-19): per update u16 pair count, then per pair u16 key length, key, u16 value length, value
  * (little endian, keys in std::map order). */
 DH_API int dh_decoder_meta_kv(dh_decoder* h, uint32_t channel, const uint8_t** data, size_t* len);
+/* The key/value records cost host time per update, so they are only kept by default for banks of <= 64 channels (the
+ * facade modules use one-channel banks); this switches them on or off for any bank from the next collect on. */
+DH_API int dh_decoder_set_meta_kv(dh_decoder* h, int enable);
 /* totals over all channels since creation */
 DH_API int dh_decoder_totals(dh_decoder* h, uint64_t* out_bytes, uint64_t* meta_bytes);
 /* events replayed and bytes copied device->host by collect since creation */

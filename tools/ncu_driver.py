@@ -1,5 +1,6 @@
 """Short single-GPU run of a pipe workload for ncu captures (never a bench value).
-usage: ncu_driver.py [channels] [samples] [steps] [proto: dmr|ysf|nxdn|dstar|pocsag]"""
+usage: ncu_driver.py [channels] [samples] [steps] [proto: dmr|ysf|nxdn|dstar|pocsag] [mode: f32|s16|shard]
+mode s16: int16 blocks (csdr convert fused into K1); mode shard: a world-1 dh_shard (adds the wire pack kernel)."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -26,10 +27,27 @@ else:
     pool = np.stack([np.resize(gen(k), nsym) for k in range(16)])
     sym = pool[np.arange(C) % 16]
     x = synth.modulate_batch(sym, L, sps=sps, levels=levels, amplitude=0.5, snr_db=15.0, seed=1, device="cuda:0")
-pipe = dh.Pipe(C, pid, max_chunk=L)
-torch.cuda.synchronize()
-for _ in range(steps):
-    pipe.process(x, n=L)
-    pipe.decoder.discard()
-torch.cuda.synchronize()
-print("done", pipe.launch_count)
+mode = sys.argv[5] if len(sys.argv) > 5 else "f32"
+if mode in ("s16", "shard"):
+    pitch = (L + 7) & ~7
+    xs = torch.zeros((C, pitch), dtype=torch.int16, device="cuda:0")
+    xs[:, :L] = torch.clamp(torch.round(x[:, :L] * 20000.0), -32768, 32767).to(torch.int16)
+    x = xs
+if mode == "shard":
+    from digiham_b200 import shard
+    sp = shard.ShardedPipe(C, pid, max_chunk=L, device="cuda:0", fmt=dh.FMT_S16)
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        sp.submit(x, L, scatter=True)
+        sp.discard_step()
+    sp.sync()
+    torch.cuda.synchronize()
+    print("done", sp.stats())
+else:
+    pipe = dh.Pipe(C, pid, max_chunk=L)
+    torch.cuda.synchronize()
+    for _ in range(steps):
+        pipe.process(x, n=L)
+        pipe.decoder.discard()
+    torch.cuda.synchronize()
+    print("done", pipe.launch_count)
