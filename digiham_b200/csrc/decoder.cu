@@ -149,6 +149,7 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
     }
     DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_decoder_create: device %d out of range", device);
     dh::DeviceGuard guard(device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", device);
     dh_decoder* h = new (std::nothrow) dh_decoder();
     DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_decoder_create: out of host memory");
     h->device = device;
@@ -181,6 +182,7 @@ int dh_decoder_create(dh_decoder** out, int device, uint32_t channels, int proto
 int dh_decoder_reserve(dh_decoder* h, size_t max_syms, uint8_t** d_buf, size_t* pitch) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_reserve: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     int rc = decoder_reserve(h, max_syms);
     if (rc != DH_OK) return rc;
     if (d_buf) *d_buf = h->d_sym + h->ops->carry_cap;
@@ -219,6 +221,7 @@ int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, co
     if (max_nsym == 0) return DH_OK;
     DH_REQUIRE(d_sym != nullptr, DH_E_INVALID, "dh_decoder_process: d_sym is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     cudaStream_t st = (cudaStream_t) stream;
     const bool zero_copy = h->d_sym && d_sym == h->d_sym + h->ops->carry_cap && sym_pitch == h->sym_pitch &&
                            max_nsym <= h->max_syms;
@@ -253,6 +256,7 @@ int dh_decoder_process(dh_decoder* h, const uint8_t* d_sym, size_t sym_pitch, co
 int dh_decoder_collect(dh_decoder* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_collect: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     return decoder_collect(h, h->active, (cudaStream_t) stream);
 }
 
@@ -265,6 +269,7 @@ int dh_decoder_select_results(dh_decoder* h, int set) {
 int dh_decoder_collect_results(dh_decoder* h, int set, void* stream) {
     DH_REQUIRE(h != nullptr && (set == 0 || set == 1), DH_E_INVALID, "dh_decoder_collect_results: bad argument");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     return decoder_collect(h, set, (cudaStream_t) stream);
 }
 
@@ -313,6 +318,7 @@ int dh_decoder_discard(dh_decoder* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_decoder_discard: handle is NULL");
     if (!h->d_counts_set[h->active]) return DH_OK;
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     DH_CUDA(cudaMemsetAsync(h->d_counts_set[h->active], 0, 3 * (size_t) h->channels * sizeof(uint32_t),
                             (cudaStream_t) stream));
     return DH_OK;
@@ -379,6 +385,7 @@ int dh_decoder_state_export(dh_decoder* h, void* h_buf, size_t cap, size_t* writ
     const dh::StateHeader hd = decoder_header(h, dev_bytes + h->channels + blob.size());
     DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_decoder_state_export: buffer too small");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     int rc = decoder_reserve(h, h->max_syms ? h->max_syms : 16);
     if (rc != DH_OK) return rc;
     cudaStream_t st = (cudaStream_t) stream;
@@ -426,6 +433,7 @@ int dh_decoder_state_import(dh_decoder* h, const void* h_buf, size_t bytes, void
                    "dh_decoder_state_import: malformed collector state of channel %u", c);
     }
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     rc = decoder_reserve(h, h->max_syms ? h->max_syms : 16);
     if (rc != DH_OK) return rc;
     cudaStream_t st = (cudaStream_t) stream;

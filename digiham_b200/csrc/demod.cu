@@ -545,6 +545,7 @@ int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_leve
     }
     DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_demod_create: device %d out of range", device);
     dh::DeviceGuard guard(device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", device);
     dh_demod* h = new (std::nothrow) dh_demod();
     DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_demod_create: out of host memory");
     h->device = device;
@@ -571,6 +572,7 @@ int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_leve
 int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reserve: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     int rc = demod_reserve(h, max_n);
     if (rc != DH_OK) return rc;
     if (d_buf) *d_buf = h->d_work[h->cur] + h->carry_cap;
@@ -589,6 +591,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     DH_REQUIRE(d_sym != nullptr && d_nsym != nullptr, DH_E_INVALID, "dh_demod_process: NULL output buffer");
     DH_REQUIRE(n <= 0x40000000u, DH_E_INVALID, "dh_demod_process: n too large");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     cudaStream_t st = (cudaStream_t) stream;
     if (n == 0) {
         DH_CUDA(cudaMemsetAsync(d_nsym, 0, (size_t) h->channels * sizeof(uint32_t), st));
@@ -700,6 +703,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
 int dh_demod_reset(dh_demod* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reset: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     DH_CUDA(cudaMemsetAsync(h->d_state, 0, (size_t) h->channels * sizeof(ChannelState), (cudaStream_t) stream));
     return DH_OK;
 }
@@ -724,6 +728,7 @@ int dh_demod_state_export(dh_demod* h, void* h_buf, size_t cap, size_t* written,
     const dh::StateHeader hd = demod_header(h);
     DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_demod_state_export: buffer too small");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     int rc = demod_reserve(h, 0);
     if (rc != DH_OK) return rc;
     cudaStream_t st = (cudaStream_t) stream;
@@ -746,6 +751,7 @@ int dh_demod_state_import(dh_demod* h, const void* h_buf, size_t bytes, void* st
     int rc = dh::check_state_header(h_buf, bytes, hd, "dh_demod_state_import");
     if (rc != DH_OK) return rc;
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     rc = demod_reserve(h, 0);
     if (rc != DH_OK) return rc;
     cudaStream_t st = (cudaStream_t) stream;

@@ -142,6 +142,7 @@ int dh_dvf_create(dh_dvf** out, int device, uint32_t channels) {
     }
     DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_dvf_create: device %d out of range", device);
     dh::DeviceGuard guard(device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", device);
     dh_dvf* h = new (std::nothrow) dh_dvf();
     DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_dvf_create: out of host memory");
     h->device = device;
@@ -166,6 +167,7 @@ int dh_dvf_process(dh_dvf* h, const int16_t* d_in, size_t in_pitch, int16_t* d_o
     DH_REQUIRE(in_pitch >= n && out_pitch >= n, DH_E_INVALID, "dh_dvf_process: pitch < n");
     DH_REQUIRE(n <= 0x7fffffffu, DH_E_INVALID, "dh_dvf_process: n too large");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     DvfParams p;
     p.in = d_in;
     p.out = d_out;
@@ -183,6 +185,7 @@ int dh_dvf_process(dh_dvf* h, const int16_t* d_in, size_t in_pitch, int16_t* d_o
 int dh_dvf_reset(dh_dvf* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_dvf_reset: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     DH_CUDA(cudaMemsetAsync(h->d_state, 0, (size_t) h->channels * sizeof(DvfState), (cudaStream_t) stream));
     return DH_OK;
 }

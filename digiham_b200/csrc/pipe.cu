@@ -97,6 +97,7 @@ int dh_pipe_create(dh_pipe** out, int device, uint32_t channels, int proto, size
     }
     if (rc == DH_OK) {
         dh::DeviceGuard guard(device);
+        DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", device);
         int lo_prio = 0, hi_prio = 0;
         cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio);
         int pa = lo_prio, pb = hi_prio;
@@ -257,6 +258,7 @@ int dh_pipe_process_device_s16(dh_pipe* h, const int16_t* d_in, size_t in_pitch,
 int dh_pipe_input_event(dh_pipe* h, void* event) {
     DH_REQUIRE(h != nullptr && event != nullptr, DH_E_INVALID, "dh_pipe_input_event: NULL argument");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     // the first kernel of a call is the only reader of the caller's block (K1, or K2 for the pipes without an RRC
     // stage); nothing else has been enqueued on its stream since
     DH_CUDA(cudaEventRecord((cudaEvent_t) event, h->last_k1_stream));
@@ -274,6 +276,7 @@ int dh_pipe_sync(dh_pipe* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_sync: handle is NULL");
     if (!h->async_pending) return DH_OK;
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     // stream b runs the last stage of every call and waits for stream a's K1 of the same call
     DH_CUDA(cudaStreamWaitEvent((cudaStream_t) stream, h->ev_done, 0));
     h->async_pending = false;
@@ -306,6 +309,7 @@ int dh_pipe_set_profiling(dh_pipe* h, int enable) {
 int dh_pipe_stage_times(dh_pipe* h, double ms[3], uint64_t* calls) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_stage_times: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     double acc[3] = {0, 0, 0};
     const size_t ncalls = h->events_used / 6;
     for (size_t c = 0; c < ncalls; c++) {
@@ -434,6 +438,7 @@ int dh_pipe_collect_step(dh_pipe* h) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_pipe_collect_step: handle is NULL");
     DH_REQUIRE(h->collected < h->submitted, DH_E_STATE, "dh_pipe_collect_step: nothing in flight");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     const int slot = (int) (h->collected & 1);
     DH_CUDA(cudaEventSynchronize(h->ev_decoded[slot]));
     // read-back on the copy-independent compute-side helper: the default stream would serialise with everything
@@ -543,6 +548,7 @@ int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, c
 int dh_pipe_read_symbols(dh_pipe* h, uint32_t channel, uint8_t* h_buf, size_t cap, size_t* count) {
     DH_REQUIRE(h != nullptr && channel < h->channels, DH_E_INVALID, "dh_pipe_read_symbols: bad handle or channel");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     if (h->async_pending) DH_CUDA(cudaStreamSynchronize(h->sb));
     uint32_t n = 0;
     DH_CUDA(cudaMemcpy(&n, h->d_nsym + channel, sizeof(n), cudaMemcpyDeviceToHost));

@@ -296,6 +296,7 @@ int rrc_build(dh_rrc** out, int device, uint32_t channels, uint32_t nz, double g
     }
     DH_REQUIRE(device >= 0 && device < ndev, DH_E_INVALID, "dh_rrc_create: device %d out of range", device);
     dh::DeviceGuard guard(device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", device);
     dh_rrc* h = new (std::nothrow) dh_rrc();
     DH_REQUIRE(h != nullptr, DH_E_NOMEM, "dh_rrc_create: out of host memory");
     h->device = device;
@@ -483,6 +484,7 @@ int dh_rrc_state_export(dh_rrc* h, void* h_buf, size_t cap, size_t* written, voi
     const dh::StateHeader hd = rrc_header(h);
     DH_REQUIRE(cap >= sizeof(hd) + hd.payload, DH_E_INVALID, "dh_rrc_state_export: buffer too small");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     std::memcpy(h_buf, &hd, sizeof(hd));
     const float* cur = h->d_hist + (size_t) h->cur * h->channels * h->nz;
     DH_CUDA(cudaMemcpyAsync(static_cast<char*>(h_buf) + sizeof(hd), cur, hd.payload, cudaMemcpyDeviceToHost,
@@ -498,6 +500,7 @@ int dh_rrc_state_import(dh_rrc* h, const void* h_buf, size_t bytes, void* stream
     int rc = dh::check_state_header(h_buf, bytes, hd, "dh_rrc_state_import");
     if (rc != DH_OK) return rc;
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     float* cur = h->d_hist + (size_t) h->cur * h->channels * h->nz;
     DH_CUDA(cudaMemcpyAsync(cur, static_cast<const char*>(h_buf) + sizeof(hd), hd.payload, cudaMemcpyHostToDevice,
                             (cudaStream_t) stream));
@@ -508,6 +511,7 @@ int dh_rrc_state_import(dh_rrc* h, const void* h_buf, size_t bytes, void* stream
 int dh_rrc_reset(dh_rrc* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_rrc_reset: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     DH_CUDA(cudaMemsetAsync(h->d_hist, 0, 2 * (size_t) h->channels * h->nz * sizeof(float), (cudaStream_t) stream));
     h->cur = 0;
     return DH_OK;

@@ -454,6 +454,7 @@ int dh_shard_collect_step(dh_shard* h) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_shard_collect_step: handle is NULL");
     DH_REQUIRE(h->collected < h->submitted, DH_E_STATE, "dh_shard_collect_step: nothing in flight");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     const int slot = (int) (h->collected & 1);
     DH_CUDA(cudaEventSynchronize(h->ev_gathered[slot]));
     h->collected++;
@@ -482,6 +483,7 @@ int dh_shard_discard_step(dh_shard* h) {
 int dh_shard_sync(dh_shard* h, void* stream) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_shard_sync: handle is NULL");
     dh::DeviceGuard guard(h->device);
+    DH_REQUIRE(guard.ok, DH_E_NODEVICE, "cannot switch to CUDA device %d", h->device);
     cudaStream_t st = (cudaStream_t) stream;
     cudaStream_t all[3] = {h->s_in, h->s_cmp, h->s_out};
     for (cudaStream_t s : all) {
