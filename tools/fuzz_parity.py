@@ -36,7 +36,7 @@ PROTOS = {
 }
 rng = np.random.default_rng(seed0)
 t_end = time.time() + budget
-stats = {k: [0, 0, 0] for k in PROTOS}   # rounds, channels, bytes compared
+stats = {k: [0, 0, 0, 0, 0] for k in PROTOS}   # rounds, channels, bytes compared, migrations, int16 rounds
 bad = 0
 rnd = 0
 while time.time() < t_end and not bad:
@@ -57,27 +57,56 @@ while time.time() < t_end and not bad:
         pipe = dh.Pipe(C, pid, max_chunk=max_chunk)
         use_async = bool(rng.integers(0, 2))
         pipe.set_async(use_async)
+        # r02: int16 ingest on the pipes with an RRC stage (csdr convert fused into K1), and a mid-stream migration
+        # of all channels to a new pipe through a state blob
+        use_s16 = name in ("dmr", "ysf", "nxdn") and bool(rng.integers(0, 2))
+        if use_s16:
+            x = torch.clamp(torch.round(x[:, :n] * 20000.0), -32768, 32767).to(torch.int16)
+            ref_in = x.cpu().numpy().astype(np.float32) / np.float32(32767)
+        else:
+            ref_in = x[:, :n].cpu().numpy()
+        migrate_at = int(rng.integers(1, 6)) if rng.random() < 0.35 else -1
+        got = [[b"", b""] for _ in range(C)]
+
+        def drain():
+            pipe.collect()
+            for ch in range(C):
+                got[ch][0] += pipe.output(ch)
+                got[ch][1] += pipe.meta(ch)
+            pipe.decoder.clear()
+
         pos, calls = 0, 0
+        unit = 8 if use_s16 else 4
         while pos < n:
             c = int(min(n - pos, rng.integers(1, max_chunk + 1)))
-            blk = torch.zeros((C, (c + 3) & ~3), dtype=torch.float32, device="cuda")
+            blk = torch.zeros((C, (c + unit - 1) // unit * unit), dtype=x.dtype, device="cuda")
             blk[:, :c] = x[:, pos:pos + c]
             pipe.process(blk, n=c)
             pipe.sync()          # blk goes out of scope
             calls += 1
             if calls % 2 == 0:
-                pipe.collect()
+                drain()
             pos += c
-        pipe.collect()
+            if calls == migrate_at:
+                drain()
+                blob = pipe.export_state()
+                pipe.close()
+                pipe = dh.Pipe(C, pid, max_chunk=max_chunk)
+                pipe.set_async(use_async)
+                pipe.import_state(blob)
+                stats[name][3] += 1
+        drain()
         pipe.set_async(False)
-        _, outs, metas = orc.pipe_batch(oid, x[:, :n].cpu().numpy(), threads=8, meta_cap=1 << 16)
+        _, outs, metas = orc.pipe_batch(oid, ref_in, threads=8, meta_cap=1 << 16)
         for ch in range(C):
-            if pipe.output(ch) != outs[ch].tobytes() or pipe.meta(ch) != metas[ch]:
-                print("MISMATCH proto=%s round=%d ch=%d C=%d n=%d max_chunk=%d async=%s: %d vs %d bytes, meta %d vs %d" % (
-                    name, rnd, ch, C, n, max_chunk, use_async, len(pipe.output(ch)), outs[ch].size, len(pipe.meta(ch)), len(metas[ch])))
+            if got[ch][0] != outs[ch].tobytes() or got[ch][1] != metas[ch]:
+                print("MISMATCH proto=%s round=%d ch=%d C=%d n=%d max_chunk=%d async=%s s16=%s migrate=%d: %d vs %d bytes, meta %d vs %d" % (
+                    name, rnd, ch, C, n, max_chunk, use_async, use_s16, migrate_at, len(got[ch][0]), outs[ch].size,
+                    len(got[ch][1]), len(metas[ch])))
                 bad += 1
                 break
             stats[name][2] += outs[ch].size + len(metas[ch])
+        stats[name][4] += int(use_s16)
         stats[name][0] += 1
         stats[name][1] += C
         pipe.close()
@@ -86,6 +115,6 @@ while time.time() < t_end and not bad:
     if rnd >= max_rounds:
         break
 for k, v in stats.items():
-    print("%-7s rounds %4d  channels %6d  bytes compared %9d" % (k, v[0], v[1], v[2]))
+    print("%-7s rounds %4d  channels %6d  bytes compared %9d  state migrations %3d  int16 rounds %3d" % (k, v[0], v[1], v[2], v[3], v[4]))
 print("fuzz: %s" % ("FAILED" if bad else "all equal"))
 sys.exit(1 if bad else 0)
