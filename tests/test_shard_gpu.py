@@ -141,3 +141,56 @@ def test_shard_two_ranks_scatter_compute_gather(s16):
     assert status == "ok" and nbytes > 27 * 50 and nlocal == 51
     status2, _, _ = q.get(timeout=10)
     assert status2 == "ok"
+
+
+def _cpp_host(tmp_path, world):
+    """examples/sharded_pipe.cpp: a C++ host (no Python, no torch in the processes) runs the sharded pipe through the
+    C ABI alone; rank 0's gathered output must equal the reference for every channel."""
+    import struct
+    import subprocess
+    root = oracle_lib.ROOT
+    exe = str(tmp_path / "sharded_pipe")
+    subprocess.run(["g++", "-std=c++17", "-O1", "-I" + os.path.join(root, "include"), "-I/usr/local/cuda/include",
+                    os.path.join(root, "examples", "sharded_pipe.cpp"), "-L" + os.path.join(root, "digiham_b200"),
+                    "-ldigiham_b200", "-Wl,-rpath," + os.path.join(root, "digiham_b200"), "-L/usr/local/cuda/lib64",
+                    "-lcudart", "-o", exe], check=True)
+    channels, n, steps = 45, 12000, 3
+    data, ref_in = _make_input(channels, n, steps, seed=47, s16=True, device="cuda")
+    s = data.cpu().numpy()                                        # [channels, n * steps]
+    blocks = np.stack([s[:, k * n:(k + 1) * n] for k in range(steps)])   # [steps][channels][n]
+    inp = str(tmp_path / "in.s16")
+    blocks.astype(np.int16).tofile(inp)
+    prefix = str(tmp_path / "res")
+    idf = str(tmp_path / "nccl.id")
+    procs = [subprocess.Popen([exe, str(r), str(world), idf, inp, str(channels), str(n), str(steps), prefix],
+                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(world)]
+    outs = [p.communicate(timeout=300) for p in procs]
+    for p, (so, se) in zip(procs, outs):
+        assert p.returncode == 0, se[-2000:]
+    assert "%d channels over %d rank(s)" % (channels, world) in outs[0][0]
+    _, ref_out, ref_meta = oracle_lib.best().pipe_batch(oracle_lib.PROTO_DMR, ref_in, threads=8, chunk=4096)
+
+    def records(path):
+        raw = open(path, "rb").read()
+        pos, res = 0, []
+        while pos < len(raw):
+            (ln,) = struct.unpack_from("<I", raw, pos)
+            res.append(raw[pos + 4:pos + 4 + ln])
+            pos += 4 + ln
+        return res
+
+    got_out, got_meta = records(prefix + ".out"), records(prefix + ".meta")
+    assert len(got_out) == channels and len(got_meta) == channels
+    for c in range(channels):
+        assert got_out[c] == ref_out[c].tobytes() and got_meta[c] == ref_meta[c], c
+    assert sum(len(o) for o in got_out) > 27 * 20
+
+
+def test_cpp_host_sharded_pipe_one_rank(tmp_path):
+    _cpp_host(tmp_path, 1)
+
+
+def test_cpp_host_sharded_pipe_two_ranks(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _cpp_host(tmp_path, 2)
