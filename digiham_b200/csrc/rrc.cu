@@ -401,6 +401,10 @@ int rrc_launch(dh_rrc* h, const void* d_in, size_t in_pitch, float* d_out, size_
         h->taps_r = r;
     }
     size_t smem = (size_t) (h->nz + tile) * sizeof(float);
+    // experiment switch: extra (unused) dynamic shared memory per CTA caps the resident CTAs per SM, to measure how much
+    // of the slowdown beside K2 / K3 is lost occupancy
+    static const size_t extra_smem = getenv("DH_RRC_EXTRA_SMEM") ? (size_t) atoi(getenv("DH_RRC_EXTRA_SMEM")) : 0;
+    if (smem + extra_smem <= 48 * 1024) smem += extra_smem;
     const int which = h->nz == 80 && h->mul_recip ? 0 : (h->nz == 160 && h->mul_recip ? 1 : 2);
     if (which == 2 && h->nz + 1 > kMaxTapsParam) smem += (size_t) (h->nz + 1) * sizeof(float);
 #define DH_LAUNCH_RRC2(RR, SS)                                                                          \
