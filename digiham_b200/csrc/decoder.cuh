@@ -109,6 +109,7 @@ struct ChannelResult {
 };
 
 class MetaReplay;
+class WorkerPool;   // result_sink.cu: persistent host threads for the per-channel replay
 
 // Where device result blocks end up on the host: per-channel byte streams + the metadata lines replayed from the
 // 16-byte event records.  One sink serves a decoder bank (its own channels) or the gathering rank of a sharded
@@ -122,6 +123,9 @@ struct ResultSink {
     size_t h_out_bytes = 0;
     DecEvent* h_ev = nullptr;
     size_t h_ev_bytes = 0;
+    WorkerPool* pool = nullptr;           // created on first use, joined by release()
+    uint8_t* d_compact = nullptr;         // device staging: the used widths of all rows, densely packed, so that the
+    size_t d_compact_bytes = 0;           // read-back is ONE contiguous copy instead of thousands of short rows
     uint64_t total_bytes = 0, total_meta = 0, total_events = 0, total_d2h = 0;
     // key/value records beside the text lines (dh_decoder_meta_kv): kept for small banks (the facade's one-channel
     // banks apply their own Serializer to them), off for large ones unless asked for (dh_decoder_set_meta_kv)

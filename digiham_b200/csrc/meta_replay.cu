@@ -285,19 +285,20 @@ class DmrReplay: public MetaReplay {
         void flush(int s, std::string& out) {
             DmrSlot& sl = slots[s];
             if (!sl.dirty) return;
-            std::map<std::string, std::string> kv;
-            kv["protocol"] = "DMR";
-            kv["slot"] = std::to_string(s);
-            if (sl.sync > 0) kv["sync"] = sl.sync == 1 ? "data" : (sl.sync == 2 ? "voice" : "unknown");
-            if (sl.type > 0) kv["type"] = sl.type == 1 ? "direct" : (sl.type == 2 ? "group" : "unknown");
-            if (sl.source > 0) kv["source"] = std::to_string(sl.source);
-            if (sl.target > 0) kv["target"] = std::to_string(sl.target);
-            if (!sl.alias.empty()) kv["talkeralias"] = sl.alias;
+            // keys in std::map (sorted) order: lat, lon, protocol, slot, source, sync, talkeralias, target, type
+            MetaLine l(out, kv_sink);
             if (sl.hasCoord) {
-                kv["lat"] = std::to_string(sl.lat);
-                kv["lon"] = std::to_string(sl.lon);
+                l.add("lat", std::to_string(sl.lat));
+                l.add("lon", std::to_string(sl.lon));
             }
-            emit(kv, out);
+            l.add("protocol", "DMR", 3);
+            l.add("slot", s ? "1" : "0", 1);
+            if (sl.source > 0) l.add_uint("source", sl.source);
+            if (sl.sync > 0) l.add("sync", sl.sync == 1 ? "data" : (sl.sync == 2 ? "voice" : "unknown"));
+            if (!sl.alias.empty()) l.add("talkeralias", sl.alias);
+            if (sl.target > 0) l.add_uint("target", sl.target);
+            if (sl.type > 0) l.add("type", sl.type == 1 ? "direct" : (sl.type == 2 ? "group" : "unknown"));
+            l.finish();
             sl.dirty = false;
         }
 };
@@ -384,18 +385,19 @@ class YsfReplay: public MetaReplay {
                 dirty = true;
                 return;
             }
-            std::map<std::string, std::string> kv;
-            kv["protocol"] = "YSF";
-            if (!mode.empty()) kv["mode"] = mode;
-            if (!destination.empty()) kv["target"] = destination;
-            if (!source.empty()) kv["source"] = source;
-            if (!up.empty()) kv["up"] = up;
-            if (!down.empty()) kv["down"] = down;
+            // keys in sorted order: down, lat, lon, mode, protocol, source, target, up
+            MetaLine l(out, kv_sink);
+            if (!down.empty()) l.add("down", down);
             if (hasCoord) {
-                kv["lat"] = std::to_string(lat);
-                kv["lon"] = std::to_string(lon);
+                l.add("lat", std::to_string(lat));
+                l.add("lon", std::to_string(lon));
             }
-            emit(kv, out);
+            if (!mode.empty()) l.add("mode", mode);
+            l.add("protocol", "YSF", 3);
+            if (!source.empty()) l.add("source", source);
+            if (!destination.empty()) l.add("target", destination);
+            if (!up.empty()) l.add("up", up);
+            l.finish();
         }
         void set(std::string& field, const std::string& v, std::string& out) {
             if (field == v) return;
@@ -548,13 +550,14 @@ class NxdnReplay: public MetaReplay {
                 dirty = true;
                 return;
             }
-            std::map<std::string, std::string> kv;
-            kv["protocol"] = "NXDN";
-            if (!sync.empty()) kv["sync"] = sync;
-            if (!type.empty()) kv["type"] = type;
-            if (source != 0) kv["source"] = std::to_string(source);
-            if (destination != 0) kv["destination"] = std::to_string(destination);
-            emit(kv, out);
+            // keys in sorted order: destination, protocol, source, sync, type
+            MetaLine l(out, kv_sink);
+            if (destination != 0) l.add_uint("destination", destination);
+            l.add("protocol", "NXDN", 4);
+            if (source != 0) l.add_uint("source", source);
+            if (!sync.empty()) l.add("sync", sync);
+            if (!type.empty()) l.add("type", type);
+            l.finish();
         }
         void setStr(std::string& field, const std::string& v, std::string& out) {
             if (field == v) return;
@@ -645,20 +648,21 @@ class DstarReplay: public MetaReplay {
                 dirty = true;
                 return;
             }
-            std::map<std::string, std::string> kv;
-            kv["protocol"] = "DSTAR";
-            if (!sync.empty()) kv["sync"] = sync;
-            if (!departure.empty()) kv["departure"] = departure;
-            if (!destination.empty()) kv["destination"] = destination;
-            if (!ourCall.empty()) kv["ourcall"] = ourCall;
-            if (!yourCall.empty()) kv["yourcall"] = yourCall;
-            if (!message.empty()) kv["message"] = message;
-            if (!dprs.empty()) kv["dprs"] = dprs;
+            // keys in sorted order: departure, destination, dprs, lat, lon, message, ourcall, protocol, sync, yourcall
+            MetaLine l(out, kv_sink);
+            if (!departure.empty()) l.add("departure", departure);
+            if (!destination.empty()) l.add("destination", destination);
+            if (!dprs.empty()) l.add("dprs", dprs);
             if (located) {
-                kv["lat"] = std::to_string(lat);
-                kv["lon"] = std::to_string(lon);
+                l.add("lat", std::to_string(lat));
+                l.add("lon", std::to_string(lon));
             }
-            emit(kv, out);
+            if (!message.empty()) l.add("message", message);
+            if (!ourCall.empty()) l.add("ourcall", ourCall);
+            l.add("protocol", "DSTAR", 5);
+            if (!sync.empty()) l.add("sync", sync);
+            if (!yourCall.empty()) l.add("yourcall", yourCall);
+            l.finish();
         }
         void set(std::string& field, const std::string& v, std::string& out) {
             if (field == v) return;

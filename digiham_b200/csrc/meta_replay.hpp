@@ -69,6 +69,62 @@ struct StateReader {
     }
 };
 
+// One metadata update written straight into the channel's text (`key:value;...\n`, reference src/lib/meta.cpp:8-17) and,
+// when asked for, into the key/value record stream — without the std::map the reference builds per update (the
+// replay of thousands of channels per step is host time that competes with the uploads of the next step).  The
+// caller adds the pairs in std::map order, i.e. sorted by key, which is the order the StringSerializer emits.
+class MetaLine {
+    public:
+        MetaLine(std::string& text, std::string* kv): text(text), kv(kv) {
+            if (kv) {
+                count_pos = kv->size();
+                kv->append(2, '\0');
+            }
+        }
+        void add(const char* key, const char* val, size_t vlen) {
+            const size_t klen = std::strlen(key);
+            if (pairs++) text.push_back(';');
+            text.append(key, klen);
+            text.push_back(':');
+            text.append(val, vlen);
+            if (kv) {
+                put16(klen);
+                kv->append(key, klen);
+                put16(vlen);
+                kv->append(val, vlen);
+            }
+        }
+        void add(const char* key, const std::string& val) { add(key, val.data(), val.size()); }
+        void add(const char* key, const char* val) { add(key, val, std::strlen(val)); }
+        void add_uint(const char* key, unsigned long long v) {
+            char buf[24];
+            int n = 0;
+            do {
+                buf[n++] = (char) ('0' + v % 10);
+                v /= 10;
+            } while (v);
+            char out[24];
+            for (int i = 0; i < n; i++) out[i] = buf[n - 1 - i];
+            add(key, out, (size_t) n);
+        }
+        void finish() {
+            text.push_back('\n');
+            if (kv) {
+                (*kv)[count_pos] = (char) (pairs & 0xFF);
+                (*kv)[count_pos + 1] = (char) ((pairs >> 8) & 0xFF);
+            }
+        }
+    private:
+        void put16(size_t v) {
+            kv->push_back((char) (v & 0xFF));
+            kv->push_back((char) ((v >> 8) & 0xFF));
+        }
+        std::string& text;
+        std::string* kv;
+        size_t count_pos = 0;
+        unsigned pairs = 0;
+};
+
 MetaReplay* make_dmr_replay();
 MetaReplay* make_ysf_replay();
 MetaReplay* make_nxdn_replay();

@@ -41,6 +41,8 @@ struct dh_pipe {
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // K1 finished reading the slot
     cudaEvent_t ev_decoded[2] = {nullptr, nullptr};    // decoder kernel of the step finished
     uint64_t submitted = 0, collected = 0;
+    // diagnostics (DH_PIPE_TRACE): timing events around the upload and the kernels of every submitted step
+    std::vector<cudaEvent_t> trace;   // groups of 4: upload start / end, kernels start / end
     // optional per-stage device timing: CUDA events around every kernel, on the stream it is launched on
     bool profiling = false;
     std::vector<cudaEvent_t> events;   // pool; groups of 6: K1 start/end, K2 start/end, decoder start/end
@@ -396,17 +398,29 @@ int pipe_submit_host(dh_pipe* h, const void* h_in, size_t in_pitch, size_t n, bo
             DH_CUDA(cudaEventCreateWithFlags(&h->ev_decoded[i], cudaEventDisableTiming));
         }
     }
+    static const bool tracing = getenv("DH_PIPE_TRACE") != nullptr;
+    auto trace_mark = [&](cudaStream_t st) {
+        if (!tracing || h->trace.size() >= 4 * 256) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        h->trace.push_back(e);
+    };
     // upload into the slot once K1 of the step that used it two submissions ago has read it
     if (h->submitted >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_copy, h->ev_consumed[slot], 0));
+    trace_mark(h->s_copy);
     int rc = upload(h, h->d_slot[slot], h_in, in_pitch, n, s16, h->s_copy);
     if (rc != DH_OK) return rc;
+    trace_mark(h->s_copy);
     DH_CUDA(cudaEventRecord(h->ev_uploaded[slot], h->s_copy));
     DH_CUDA(cudaStreamWaitEvent(h->s_compute, h->ev_uploaded[slot], 0));
+    trace_mark(h->s_compute);
     // results of this step go to the result set of its parity
     rc = dh_decoder_select_results(h->decoder, slot);
     if (rc != DH_OK) return rc;
     rc = run_stages(h, h->d_slot[slot], host_pitch_of(h, s16), n, h->s_compute, h->s_compute, nullptr, nullptr, s16);
     if (rc != DH_OK) return rc;
+    trace_mark(h->s_compute);
     // K1 is the only reader of the slot, but the stages are serialised on one stream anyway
     DH_CUDA(cudaEventRecord(h->ev_consumed[slot], h->s_compute));
     DH_CUDA(cudaEventRecord(h->ev_decoded[slot], h->s_compute));
@@ -570,6 +584,16 @@ void dh_pipe_destroy(dh_pipe* h) {
     if (!h) return;
     {
         dh::DeviceGuard guard(h->device);
+        if (!h->trace.empty()) {
+            cudaDeviceSynchronize();
+            const size_t steps = h->trace.size() / 4;
+            for (size_t k = 0; k < steps; k++) {
+                float t[4] = {0, 0, 0, 0};
+                for (int j = 0; j < 4; j++) cudaEventElapsedTime(&t[j], h->trace[0], h->trace[4 * k + j]);
+                fprintf(stderr, "[pipe trace] step %3zu: upload %9.3f .. %9.3f ms, kernels %9.3f .. %9.3f ms\n", k, t[0], t[1], t[2], t[3]);
+            }
+            for (cudaEvent_t e : h->trace) cudaEventDestroy(e);
+        }
         for (cudaEvent_t e : h->events) cudaEventDestroy(e);
         for (cudaEvent_t e : h->ev_k1) cudaEventDestroy(e);
         for (cudaEvent_t e : h->ev_k2) cudaEventDestroy(e);

@@ -7,15 +7,115 @@
 // (decoder.cu) for its own channels and by the gathering rank of a sharded pipe (shard.cu) for every rank's.
 #include "decoder_ops.hpp"
 
+#include <emmintrin.h>
+
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 #include <vector>
 
 namespace dh {
 
+// Persistent worker threads for the replay pass.  They are created once per sink: spawning threads per collect means
+// eight stack mmap / munmap pairs and fresh malloc arenas every step, and that address-space churn (TLB shoot-downs,
+// IOMMU invalidations under the pinned mappings) was measured to slow the concurrent host -> device upload of the
+// next step by 5 % (7.08 -> 7.45 ms per 393 MB block).
+class WorkerPool {
+    public:
+        explicit WorkerPool(unsigned n): count(n) {
+            for (unsigned t = 1; t < n; t++) threads.emplace_back([this, t] { loop(t); });
+        }
+        ~WorkerPool() {
+            {
+                std::lock_guard<std::mutex> lock(m);
+                quit = true;
+                generation++;
+            }
+            wake.notify_all();
+            for (auto& t : threads) t.join();
+        }
+        unsigned size() const { return count; }
+        // runs fn(t) for t in [0, size()): t = 0 on the calling thread, the others on the workers; returns when all are done
+        void parallel(const std::function<void(unsigned)>& fn) {
+            {
+                std::lock_guard<std::mutex> lock(m);
+                job = &fn;
+                pending = count - 1;
+                generation++;
+            }
+            wake.notify_all();
+            fn(0);
+            std::unique_lock<std::mutex> lock(m);
+            done.wait(lock, [this] { return pending == 0; });
+            job = nullptr;
+        }
+    private:
+        void loop(unsigned t) {
+            uint64_t seen = 0;
+            for (;;) {
+                const std::function<void(unsigned)>* fn = nullptr;
+                {
+                    std::unique_lock<std::mutex> lock(m);
+                    wake.wait(lock, [&] { return generation != seen; });
+                    seen = generation;
+                    if (quit) return;
+                    fn = job;
+                }
+                (*fn)(t);
+                {
+                    std::lock_guard<std::mutex> lock(m);
+                    if (--pending == 0) done.notify_one();
+                }
+            }
+        }
+        unsigned count;
+        std::vector<std::thread> threads;
+        std::mutex m;
+        std::condition_variable wake, done;
+        const std::function<void(unsigned)>* job = nullptr;
+        unsigned pending = 0;
+        uint64_t generation = 0;
+        bool quit = false;
+};
+
 namespace {
+
+// dst[r][0 .. w16) = src[r][0 .. w16) for r < rows, in 16-byte units (both pitches are multiples of 16)
+__global__ void compact_rows_kernel(const uint4* __restrict__ src, size_t src_pitch16, uint4* __restrict__ dst, uint32_t w16,
+                                    uint32_t rows) {
+    const size_t total = (size_t) rows * w16;
+    for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t) gridDim.x * blockDim.x) {
+        const size_t r = i / w16, c = i - r * w16;
+        dst[i] = src[r * src_pitch16 + c];
+    }
+}
+
+// Evicts [p, p + n) from the CPU caches.  The staging buffers are written by the GPU's copy engine every step; if
+// the lines the replay has just read are still cached, every one of those inbound PCIe writes has to invalidate a
+// line in a CPU cache first, and that stalls the root complex long enough to slow the host -> device upload that
+// runs at the same time: measured 7.08 -> 7.40 ms per 393 MB block, with nothing but 3 MB of reads as the cause
+// (tools/pipe_trace_run.py).  Flushing after use keeps the next step's writes snoop-free.
+inline void flush_lines(const void* p, size_t n) {
+    if (n == 0) return;
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(p) & ~(uintptr_t) 63;
+    const uintptr_t hi = reinterpret_cast<uintptr_t>(p) + n;
+    for (uintptr_t a = lo; a < hi; a += 64) _mm_clflush(reinterpret_cast<const void*>(a));
+}
+
+int grow_device(uint8_t** p, size_t* have, size_t need) {
+    if (need <= *have) return DH_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *have = 0;
+    need = need + need / 2 + 4096;
+    DH_CUDA(cudaMalloc((void**) p, need));
+    *have = need;
+    return DH_OK;
+}
 
 int grow_pinned(void** p, size_t* have, size_t need) {
     if (need <= *have) return DH_OK;
@@ -68,6 +168,7 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
     DH_REQUIRE(total <= channels, DH_E_INVALID, "result sink: more channels than the sink holds");
     if (total == 0) return DH_OK;
     static const bool timing = getenv("DH_SINK_TIMING") != nullptr;   // diagnostics: pass times on stderr
+    static const bool no_flush = getenv("DH_SINK_NO_FLUSH") != nullptr;   // A/B switch for the cache-line flush below
     const auto t0 = std::chrono::steady_clock::now();
     // pass 1: the per-channel counts of every block
     for (int b = 0; b < nblocks; b++) {
@@ -93,33 +194,46 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
         DH_REQUIRE(max_out <= out_pitch && max_ev <= ev_pitch, DH_E_STATE,
                    "result sink: device counts exceed the slot widths (%u > %zu or %u > %zu)", max_out, out_pitch, max_ev,
                    ev_pitch);
-        plan[b].max_out = max_out;
+        // row widths in the dense staging: bytes rounded up to 16 (the rows are copied in 16-byte units)
+        plan[b].max_out = (max_out + 15u) & ~15u;
         plan[b].max_ev = max_ev;
         plan[b].out_off = out_bytes;
         plan[b].ev_off = ev_records;
-        out_bytes += (size_t) n * max_out;
+        out_bytes += (size_t) n * plan[b].max_out;
         ev_records += (size_t) n * max_ev;
     }
     if (flags_out) *flags_out |= any_flags;
-    // pass 2: the used widths of the byte rows and event rows of every block
+    DH_REQUIRE(out_pitch % 16 == 0, DH_E_INVALID, "result sink: byte rows must have a pitch that is a multiple of 16");
+    // pass 2: the used widths of all rows are packed densely on the device (a 2-D copy of thousands of sub-kilobyte
+    // rows keeps a copy engine busy for a third of a millisecond and stalls the uploads that share it), then ONE
+    // contiguous copy per kind brings them to the host
+    const size_t ev_bytes = ev_records * sizeof(DecEvent);
     int rc = grow_pinned((void**) &h_out, &h_out_bytes, out_bytes);
-    if (rc == DH_OK) rc = grow_pinned((void**) &h_ev, &h_ev_bytes, ev_records * sizeof(DecEvent));
+    if (rc == DH_OK) rc = grow_pinned((void**) &h_ev, &h_ev_bytes, ev_bytes);
+    if (rc == DH_OK) rc = grow_device(&d_compact, &d_compact_bytes, out_bytes + ev_bytes);
     if (rc != DH_OK) return rc;
     for (int b = 0; b < nblocks; b++) {
         const uint32_t n = blocks[b].n;
         if (plan[b].max_out) {
-            DH_CUDA(cudaMemcpy2DAsync(h_out + plan[b].out_off, plan[b].max_out, blocks[b].d_out, out_pitch, plan[b].max_out, n,
-                                      cudaMemcpyDeviceToHost, st));
+            const uint32_t w16 = plan[b].max_out / 16;
+            const unsigned grid = (unsigned) std::min<size_t>(((size_t) n * w16 + 255) / 256, 148 * 8);
+            compact_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(blocks[b].d_out), out_pitch / 16,
+                                                     reinterpret_cast<uint4*>(d_compact + plan[b].out_off), w16, n);
         }
         if (plan[b].max_ev) {
-            const size_t w = (size_t) plan[b].max_ev * sizeof(DecEvent);
-            DH_CUDA(cudaMemcpy2DAsync(h_ev + plan[b].ev_off, w, blocks[b].d_ev, ev_pitch * sizeof(DecEvent), w, n,
-                                      cudaMemcpyDeviceToHost, st));
+            const uint32_t w16 = plan[b].max_ev;   // one event record = 16 bytes
+            const unsigned grid = (unsigned) std::min<size_t>(((size_t) n * w16 + 255) / 256, 148 * 8);
+            compact_rows_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4*>(blocks[b].d_ev), ev_pitch,
+                                                     reinterpret_cast<uint4*>(d_compact + out_bytes + plan[b].ev_off * sizeof(DecEvent)),
+                                                     w16, n);
         }
     }
+    DH_CUDA(cudaGetLastError());
+    if (out_bytes) DH_CUDA(cudaMemcpyAsync(h_out, d_compact, out_bytes, cudaMemcpyDeviceToHost, st));
+    if (ev_bytes) DH_CUDA(cudaMemcpyAsync(h_ev, d_compact + out_bytes, ev_bytes, cudaMemcpyDeviceToHost, st));
     DH_CUDA(cudaStreamSynchronize(st));
     const auto t1 = std::chrono::steady_clock::now();
-    total_d2h += out_bytes + ev_records * sizeof(DecEvent);
+    total_d2h += out_bytes + ev_bytes;
     // pass 3: per-channel appends and metadata replay are independent: one parallel pass over all blocks
     auto work = [&](int b, uint32_t c_lo, uint32_t c_hi, uint64_t* sums) {
         const uint32_t n = blocks[b].n;
@@ -142,9 +256,18 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
                 sums[1] += r.meta.size() - before;
             }
         }
+        if (!no_flush) {
+            flush_lines(h_out + plan[b].out_off + (size_t) c_lo * max_out, (size_t) (c_hi - c_lo) * max_out);
+            flush_lines(h_ev + plan[b].ev_off + (size_t) c_lo * max_ev, (size_t) (c_hi - c_lo) * max_ev * sizeof(DecEvent));
+            flush_lines(out_len + c_lo, (size_t) (c_hi - c_lo) * sizeof(uint32_t));
+            flush_lines(ev_len + c_lo, (size_t) (c_hi - c_lo) * sizeof(uint32_t));
+            flush_lines(out_len + 2 * (size_t) n + c_lo, (size_t) (c_hi - c_lo) * sizeof(uint32_t));
+        }
     };
     unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), total >= 16384 ? 24u : 8u);
     if (total < 256) nthreads = 1;
+    static const int forced_threads = getenv("DH_SINK_THREADS") ? atoi(getenv("DH_SINK_THREADS")) : 0;   // tuning switch
+    if (forced_threads > 0) nthreads = (unsigned) forced_threads;
     std::vector<uint64_t> sums((size_t) nthreads * 8, 0);   // 8 slots apart: no false sharing
     // thread t takes the t-th slice of the concatenated channel list
     auto run = [&](unsigned t) {
@@ -163,9 +286,12 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
     if (nthreads == 1) {
         run(0);
     } else {
-        std::vector<std::thread> pool;
-        for (unsigned t = 0; t < nthreads; t++) pool.emplace_back(run, t);
-        for (auto& t : pool) t.join();
+        if (pool && pool->size() != nthreads) {
+            delete pool;
+            pool = nullptr;
+        }
+        if (!pool) pool = new WorkerPool(nthreads);
+        pool->parallel(run);
     }
     uint64_t ev_now = 0, meta_now = 0;
     for (unsigned t = 0; t < nthreads; t++) {
@@ -194,9 +320,14 @@ void ResultSink::clear() {
 }
 
 void ResultSink::release() {
+    delete pool;
+    pool = nullptr;
     if (h_counts) cudaFreeHost(h_counts);
     if (h_out) cudaFreeHost(h_out);
     if (h_ev) cudaFreeHost(h_ev);
+    cudaFree(d_compact);
+    d_compact = nullptr;
+    d_compact_bytes = 0;
     h_counts = nullptr;
     h_out = nullptr;
     h_ev = nullptr;

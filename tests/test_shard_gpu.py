@@ -194,3 +194,32 @@ def test_cpp_host_sharded_pipe_two_ranks(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     _cpp_host(tmp_path, 2)
+
+
+@pytest.mark.parametrize("name,s16", [("ysf", True), ("nxdn", False), ("dstar", False), ("pocsag", False)])
+def test_shard_world1_other_protocols(name, s16):
+    """The sharded pipe is protocol-agnostic (wire slots sized from each protocol's per-step bounds; the FSK pipes have no
+    RRC stage, so their first kernel — the demodulator — is the reader of the scattered block)."""
+    import bench
+    import digiham_b200 as dh
+    from digiham_b200 import shard
+    C, n, steps = 40, 24000, 3
+    dh_proto, orc_proto = bench.proto_ids(name)
+    x = bench.workload_signal(name, C, n * steps, 5, "cuda")[:, :n * steps].contiguous()
+    if s16:
+        data = torch.clamp(torch.round(x * 20000.0), -32768, 32767).to(torch.int16)
+        ref_in = data.cpu().numpy().astype(np.float32) / np.float32(32767)
+    else:
+        data, ref_in = x, x.cpu().numpy()
+    sp = shard.ShardedPipe(C, dh_proto, max_chunk=n, device="cuda:0", fmt=dh.FMT_S16 if s16 else dh.FMT_F32)
+    _run_sharded(sp, data, n, steps, sp.pitch, scatter=True)
+    _, outs, metas = oracle_lib.best().pipe_batch(orc_proto, ref_in, threads=8, chunk=4096, meta_cap=1 << 15)
+    assert sum(len(o) + len(m) for o, m in zip(outs, metas)) > 0
+    for c in range(C):
+        assert sp.output(c) == outs[c].tobytes() and sp.meta(c) == metas[c], (name, c)
+    sp.close()
+    if name == "pocsag":
+        with pytest.raises(dh.DhError):      # no RRC stage to fuse the int16 conversion into
+            bad = shard.ShardedPipe(C, dh_proto, max_chunk=n, device="cuda:0", fmt=dh.FMT_S16)
+            blk = torch.zeros((C, bad.pitch), dtype=torch.int16, device="cuda")
+            bad.submit(blk, n, scatter=True)
