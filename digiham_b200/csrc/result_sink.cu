@@ -264,7 +264,7 @@ int ResultSink::ingest_blocks(const Block* blocks, int nblocks, size_t out_pitch
             flush_lines(out_len + 2 * (size_t) n + c_lo, (size_t) (c_hi - c_lo) * sizeof(uint32_t));
         }
     };
-    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), total >= 16384 ? 24u : 8u);
+    unsigned nthreads = std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), total >= 32768 ? 32u : (total >= 16384 ? 24u : 8u));
     if (total < 256) nthreads = 1;
     static const int forced_threads = getenv("DH_SINK_THREADS") ? atoi(getenv("DH_SINK_THREADS")) : 0;   // tuning switch
     if (forced_threads > 0) nthreads = (unsigned) forced_threads;

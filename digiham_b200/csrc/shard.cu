@@ -323,7 +323,9 @@ int dh_shard_create(dh_shard** out, void* nccl_comm, int rank, int world, int ro
     for (int i = 0; i < 2; i++) {
         DH_TRY(cudaEventCreateWithFlags(&h->ev_consumed[i], cudaEventDisableTiming));
         DH_TRY(cudaEventCreateWithFlags(&h->ev_packed[i], cudaEventDisableTiming));
-        DH_TRY(cudaEventCreateWithFlags(&h->ev_gathered[i], cudaEventDisableTiming));
+        // blocking sync: the ranks that only wait in dh_shard_collect_step sleep instead of spinning on a core the
+        // gathering rank's replay threads could use
+        DH_TRY(cudaEventCreateWithFlags(&h->ev_gathered[i], cudaEventDisableTiming | cudaEventBlockingSync));
         if (rank != root) {
             DH_TRY(cudaMalloc(&h->d_slot[i], (size_t) h->n_local * h->pitch * h->elem));
             DH_TRY(cudaMemset(h->d_slot[i], 0, (size_t) h->n_local * h->pitch * h->elem));
