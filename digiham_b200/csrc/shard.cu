@@ -3,8 +3,11 @@
 // Channels never interact (one module instance per channel in the reference, examples/dmr-decoder.sh:19-23), so
 // rank r of R owns the contiguous channel range [r*N/R, (r+1)*N/R) and runs an ordinary dh_pipe on it.  The only
 // exchange steps are the two the ingest layout forces (BASELINE configs[3]):
-//   scatter  the ingest (root) rank holds the sample block of ALL channels and sends every peer its rows
-//            (grouped ncclSend / ncclRecv over NVLink, float32 or int16 samples);
+//   scatter  the ingest (root) rank holds the sample block of ALL channels and hands every peer its rows (float32 or
+//            int16 samples): the root maps the peers' input slots through CUDA IPC and writes the rows with one
+//            copy-engine transfer per peer over NVLink (no SM is spent on it, all peers' copies run side by side),
+//            NCCL only carries the two 4-byte tokens per peer and step that order them ("slot free" / "rows landed");
+//            grouped ncclSend / ncclRecv of the rows themselves is the fallback when the slots cannot be mapped;
 //   gather   every rank packs the decoder results of the step — fixed-slot byte rows, 16-byte metadata event records,
 //            per-channel counts — into one wire block, trimmed to the per-step slot widths, and sends it to the root,
 //            which feeds all of them through one host-side result sink (result_sink.cu) in global channel order.
@@ -20,6 +23,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <new>
@@ -164,6 +168,14 @@ struct dh_shard {
     dh_decoder* dec = nullptr;
     cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr, s_back = nullptr;
     void* d_slot[2] = {nullptr, nullptr};          // received input blocks (ranks other than the root)
+    // scatter through peer memory: the root's views of every peer's two slots (cudaIpcOpenMemHandle), one copy stream
+    // per peer so that the copy engines work on all peers at once, and the 4-byte NCCL tokens that order the copies
+    bool ipc_scatter = false;
+    std::vector<void*> peer_slot[2];
+    std::vector<cudaStream_t> s_peer;
+    std::vector<cudaEvent_t> ev_peer;
+    cudaEvent_t ev_ready = nullptr;
+    uint32_t* d_token = nullptr;                    // [2 * world] scratch for the tokens
     cudaEvent_t ev_user = nullptr, ev_scattered = nullptr, ev_computed = nullptr, ev_join = nullptr;
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // first kernel of the step has read its input block
     cudaEvent_t ev_packed[2] = {nullptr, nullptr};     // result set of the step has been packed (and reset)
@@ -177,6 +189,84 @@ struct dh_shard {
     bool sink_ready = false;
     uint64_t submitted = 0, collected = 0, packs = 0;
 };
+
+namespace {
+
+// Collective (all ranks, during dh_shard_create): the peers publish CUDA IPC handles of their two input slots, the root
+// maps them and tells everybody whether the scatter can go through peer memory.  Any failure on the way (no peer
+// access, IPC refused by the platform, DH_SHARD_NO_IPC set) just selects the NCCL data path.
+int setup_ipc_scatter(dh_shard* h) {
+    const int world = h->world, rank = h->rank, root = h->root;
+    const bool is_root = rank == root;
+    DH_CUDA(cudaMalloc(&h->d_token, 2 * (size_t) world * sizeof(uint32_t)));
+    DH_CUDA(cudaMemset(h->d_token, 0, 2 * (size_t) world * sizeof(uint32_t)));
+    DH_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
+    struct Handles {
+        cudaIpcMemHandle_t slot[2];
+        uint32_t ok;
+        uint32_t pad[3];
+    };
+    Handles* d_handles = nullptr;
+    DH_CUDA(cudaMalloc(&d_handles, (size_t) world * sizeof(Handles)));
+    std::vector<Handles> all((size_t) world);
+    uint32_t usable = getenv("DH_SHARD_NO_IPC") ? 0u : 1u;
+    if (!is_root) {
+        Handles mine;
+        std::memset(&mine, 0, sizeof(mine));
+        mine.ok = usable;
+        for (int i = 0; i < 2 && mine.ok; i++) {
+            if (cudaIpcGetMemHandle(&mine.slot[i], h->d_slot[i]) != cudaSuccess) {
+                cudaGetLastError();
+                mine.ok = 0;
+            }
+        }
+        DH_CUDA(cudaMemcpyAsync(d_handles + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->s_in));
+        DH_NCCL(nccl().Send(d_handles + rank, sizeof(Handles), ncclInt8, root, h->comm_in, h->s_in));
+        // the root's verdict
+        DH_NCCL(nccl().Recv(h->d_token, sizeof(uint32_t), ncclInt8, root, h->comm_in, h->s_in));
+        DH_CUDA(cudaMemcpyAsync(&usable, h->d_token, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_in));
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+    } else {
+        DH_NCCL(nccl().GroupStart());
+        for (int r = 0; r < world; r++)
+            if (r != root) DH_NCCL(nccl().Recv(d_handles + r, sizeof(Handles), ncclInt8, r, h->comm_in, h->s_in));
+        DH_NCCL(nccl().GroupEnd());
+        DH_CUDA(cudaMemcpyAsync(all.data(), d_handles, (size_t) world * sizeof(Handles), cudaMemcpyDeviceToHost, h->s_in));
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+        for (int i = 0; i < 2; i++) h->peer_slot[i].assign((size_t) world, nullptr);
+        for (int r = 0; r < world && usable; r++) {
+            if (r == root) continue;
+            if (!all[r].ok) usable = 0;
+            for (int i = 0; i < 2 && usable; i++) {
+                if (cudaIpcOpenMemHandle(&h->peer_slot[i][r], all[r].slot[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    cudaGetLastError();
+                    h->peer_slot[i][r] = nullptr;
+                    usable = 0;
+                }
+            }
+        }
+        if (usable) {
+            h->s_peer.assign((size_t) world, nullptr);
+            h->ev_peer.assign((size_t) world, nullptr);
+            for (int r = 0; r < world; r++) {
+                if (r == root) continue;
+                DH_CUDA(cudaStreamCreateWithFlags(&h->s_peer[r], cudaStreamNonBlocking));
+                DH_CUDA(cudaEventCreateWithFlags(&h->ev_peer[r], cudaEventDisableTiming));
+            }
+        }
+        DH_CUDA(cudaMemcpyAsync(h->d_token, &usable, sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_in));
+        DH_NCCL(nccl().GroupStart());
+        for (int r = 0; r < world; r++)
+            if (r != root) DH_NCCL(nccl().Send(h->d_token, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+        DH_NCCL(nccl().GroupEnd());
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+    }
+    cudaFree(d_handles);
+    h->ipc_scatter = usable != 0;
+    return DH_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -353,6 +443,10 @@ int dh_shard_create(dh_shard** out, void* nccl_comm, int rank, int world, int ro
             return fail(DH_E_NCCL);
         }
     }
+    if (world > 1) {
+        rc = setup_ipc_scatter(h);
+        if (rc != DH_OK) return fail(rc);
+    }
     *out = h;
     return DH_OK;
 }
@@ -387,7 +481,37 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
         DH_CUDA(cudaEventRecord(h->ev_user, (cudaStream_t) stream));
         DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_user, 0));
     }
-    if (scatter) {
+    if (scatter && h->ipc_scatter) {
+        // tokens: peer -> root "my slot is free", root -> peer "your rows have landed"; the rows themselves are written
+        // into the peers' slots by the root's copy engines, one stream per peer
+        uint32_t* tok_ready = h->d_token;               // root: [world] received; peer: the one it sends
+        uint32_t* tok_done = h->d_token + h->world;
+        if (is_root) {
+            DH_NCCL(nccl().GroupStart());
+            for (int r = 0; r < h->world; r++)
+                if (r != h->root) DH_NCCL(nccl().Recv(tok_ready + r, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+            DH_NCCL(nccl().GroupEnd());
+            DH_CUDA(cudaEventRecord(h->ev_ready, h->s_in));
+            for (int r = 0; r < h->world; r++) {
+                if (r == h->root) continue;
+                DH_CUDA(cudaStreamWaitEvent(h->s_peer[r], h->ev_ready, 0));
+                DH_CUDA(cudaMemcpyAsync(h->peer_slot[slot][r], in_local + h->lo_of[r] * row_bytes,
+                                        (size_t) h->n_of[r] * row_bytes, cudaMemcpyDeviceToDevice, h->s_peer[r]));
+                DH_CUDA(cudaEventRecord(h->ev_peer[r], h->s_peer[r]));
+                DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_peer[r], 0));
+            }
+            DH_NCCL(nccl().GroupStart());
+            for (int r = 0; r < h->world; r++)
+                if (r != h->root) DH_NCCL(nccl().Send(tok_done + r, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+            DH_NCCL(nccl().GroupEnd());
+            in_local += h->lo_of[h->root] * row_bytes;
+        } else {
+            if (k >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_consumed[slot], 0));
+            DH_NCCL(nccl().Send(tok_ready, sizeof(uint32_t), ncclInt8, h->root, h->comm_in, h->s_in));
+            DH_NCCL(nccl().Recv(tok_done, sizeof(uint32_t), ncclInt8, h->root, h->comm_in, h->s_in));
+            in_local = static_cast<const char*>(h->d_slot[slot]);
+        }
+    } else if (scatter) {
         if (is_root) {
             DH_NCCL(nccl().GroupStart());
             for (int r = 0; r < h->world; r++) {
@@ -407,7 +531,8 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
     DH_CUDA(cudaEventRecord(h->ev_scattered, h->s_in));
 
     // ---- the pipe of this rank's channels (stream s_cmp orders the input, kernels on the pipe's own streams) -------
-    DH_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_scattered, 0));
+    // the root's own rows are already in place: its kernels only wait for the caller's stream, not for the scatter
+    DH_CUDA(cudaStreamWaitEvent(h->s_cmp, scatter && is_root ? h->ev_user : h->ev_scattered, 0));
     if (k >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_cmp, h->ev_packed[slot], 0));   // result set k & 1 is free again
     int rc = dh_decoder_select_results(h->dec, slot);
     if (rc != DH_OK) return rc;
@@ -517,6 +642,8 @@ int dh_shard_clear(dh_shard* h) {
     return DH_OK;
 }
 
+int dh_shard_scatter_path(const dh_shard* h) { return h ? (h->world > 1 ? (h->ipc_scatter ? 2 : 1) : 0) : 0; }
+
 int dh_shard_stats(dh_shard* h, uint64_t* launches, uint64_t* wire_bytes_per_step, uint64_t* d2h_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_shard_stats: handle is NULL");
     if (launches) *launches = dh_pipe_launch_count(h->pipe) + h->packs;
@@ -535,6 +662,15 @@ void dh_shard_destroy(dh_shard* h) {
     dh_pipe_destroy(h->pipe);
     {
         dh::DeviceGuard guard(h->device);
+        for (int i = 0; i < 2; i++)
+            for (void* p : h->peer_slot[i])
+                if (p) cudaIpcCloseMemHandle(p);
+        for (cudaStream_t s : h->s_peer)
+            if (s) cudaStreamDestroy(s);
+        for (cudaEvent_t e : h->ev_peer)
+            if (e) cudaEventDestroy(e);
+        if (h->ev_ready) cudaEventDestroy(h->ev_ready);
+        cudaFree(h->d_token);
         for (int i = 0; i < 2; i++) {
             cudaFree(h->d_slot[i]);
             cudaFree(h->d_wire[i]);

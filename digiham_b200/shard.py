@@ -127,6 +127,11 @@ class ShardedPipe:
     def clear(self):
         check(lib().dh_shard_clear(self._h))
 
+    @property
+    def scatter_path(self):
+        """0 = single rank, 1 = NCCL send / recv, 2 = copy engines into IPC-mapped peer slots."""
+        return lib().dh_shard_scatter_path(self._h)
+
     def stats(self):
         """(kernels launched by this rank, bytes of its wire block per step, bytes read back on the root)."""
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

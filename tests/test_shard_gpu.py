@@ -76,7 +76,11 @@ def test_shard_world1_pack_and_sink(s16):
     sp.close()
 
 
-def _worker(rank, world, port, channels, n, steps, s16, q):
+def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False):
+    if no_ipc:
+        os.environ["DH_SHARD_NO_IPC"] = "1"
+    else:
+        os.environ.pop("DH_SHARD_NO_IPC", None)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     import torch.distributed as dist
@@ -96,7 +100,7 @@ def _worker(rank, world, port, channels, n, steps, s16, q):
             _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, ref_in, threads=8, chunk=4096)
             bad = [c for c in range(channels)
                    if sp.output(c) != outs[c].tobytes() or sp.meta(c) != metas[c]]
-            q.put(("ok" if not bad else "mismatch %s" % bad[:8], sum(len(o) for o in outs), sp.hi - sp.lo))
+            q.put(("ok" if not bad else "mismatch %s" % bad[:8], sum(len(o) for o in outs), sp.hi - sp.lo, sp.scatter_path))
         # second phase on the same object: every rank feeds its own rows (no scatter), results still gathered
         sp.clear()
         lo, hi = sp.lo, sp.hi
@@ -122,8 +126,10 @@ def _worker(rank, world, port, channels, n, steps, s16, q):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("s16", [False, True])
-def test_shard_two_ranks_scatter_compute_gather(s16):
+@pytest.mark.parametrize("s16,no_ipc", [(False, False), (True, False), (False, True), (True, True)])
+def test_shard_two_ranks_scatter_compute_gather(s16, no_ipc):
+    """Both scatter paths: the root's copy engines writing into the IPC-mapped peer slots (default) and NCCL send / recv
+    of the rows (DH_SHARD_NO_IPC=1, also the fallback where the slots cannot be mapped)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -131,14 +137,15 @@ def test_shard_two_ranks_scatter_compute_gather(s16):
     q = ctx.Queue()
     port = _free_port()
     channels, n, steps = 101, 12000, 4     # ragged split: 51 + 50 channels
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, channels, n, steps, s16, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, channels, n, steps, s16, q, no_ipc)) for r in range(2)]
     for p in procs:
         p.start()
     for p in procs:
         p.join(timeout=300)
         assert p.exitcode == 0
-    status, nbytes, nlocal = q.get(timeout=10)
+    status, nbytes, nlocal, path = q.get(timeout=10)
     assert status == "ok" and nbytes > 27 * 50 and nlocal == 51
+    assert path == (1 if no_ipc else 2), "scatter path %d" % path
     status2, _, _ = q.get(timeout=10)
     assert status2 == "ok"
 
