@@ -176,6 +176,7 @@ struct dh_shard {
     std::vector<cudaEvent_t> ev_peer;
     cudaEvent_t ev_ready = nullptr;
     uint32_t* d_token = nullptr;                    // [2 * world] scratch for the tokens
+    std::vector<cudaEvent_t> trace;                 // diagnostics (DH_SHARD_TRACE): 6 timing events per step
     cudaEvent_t ev_user = nullptr, ev_scattered = nullptr, ev_computed = nullptr, ev_join = nullptr;
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // first kernel of the step has read its input block
     cudaEvent_t ev_packed[2] = {nullptr, nullptr};     // result set of the step has been packed (and reset)
@@ -396,9 +397,14 @@ int dh_shard_create(dh_shard** out, void* nccl_comm, int rank, int world, int ro
             return fail((int) e__);                                                           \
         }                                                                                     \
     } while (0)
-    DH_TRY(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    // The communication streams get the highest priority: a NCCL kernel launched behind an 80 000-CTA FIR grid of
+    // equal priority is only dispatched in that grid's tail, which turned the 4-byte ordering tokens of the scatter
+    // into 2-3 ms waits (DH_SHARD_TRACE timeline)
+    int lo_prio = 0, hi_prio = 0;
+    DH_TRY(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+    DH_TRY(cudaStreamCreateWithPriority(&h->s_in, cudaStreamNonBlocking, hi_prio));
     DH_TRY(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
-    DH_TRY(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    DH_TRY(cudaStreamCreateWithPriority(&h->s_out, cudaStreamNonBlocking, hi_prio));
     DH_TRY(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
     DH_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
     DH_TRY(cudaEventCreateWithFlags(&h->ev_scattered, cudaEventDisableTiming));
@@ -473,6 +479,14 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
     DH_REQUIRE(guard.ok, DH_E_NODEVICE, "dh_shard_submit_device: cannot switch to device %d", h->device);
     const uint64_t k = h->submitted;
     const int slot = (int) (k & 1);
+    static const bool tracing = getenv("DH_SHARD_TRACE") != nullptr;
+    auto trace_mark = [&](cudaStream_t st) {
+        if (!tracing || h->trace.size() >= 6 * 64) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        h->trace.push_back(e);
+    };
     const size_t row_bytes = h->pitch * h->elem;
     const char* in_local = static_cast<const char*>(d_in);
 
@@ -481,6 +495,7 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
         DH_CUDA(cudaEventRecord(h->ev_user, (cudaStream_t) stream));
         DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_user, 0));
     }
+    trace_mark(h->s_in);   // 0: scatter phase starts
     if (scatter && h->ipc_scatter) {
         // tokens: peer -> root "my slot is free", root -> peer "your rows have landed"; the rows themselves are written
         // into the peers' slots by the root's copy engines, one stream per peer
@@ -492,6 +507,7 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
                 if (r != h->root) DH_NCCL(nccl().Recv(tok_ready + r, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
             DH_NCCL(nccl().GroupEnd());
             DH_CUDA(cudaEventRecord(h->ev_ready, h->s_in));
+            trace_mark(h->s_in);   // 1: all peers ready
             for (int r = 0; r < h->world; r++) {
                 if (r == h->root) continue;
                 DH_CUDA(cudaStreamWaitEvent(h->s_peer[r], h->ev_ready, 0));
@@ -500,6 +516,7 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
                 DH_CUDA(cudaEventRecord(h->ev_peer[r], h->s_peer[r]));
                 DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_peer[r], 0));
             }
+            trace_mark(h->s_in);   // 2: copies landed
             DH_NCCL(nccl().GroupStart());
             for (int r = 0; r < h->world; r++)
                 if (r != h->root) DH_NCCL(nccl().Send(tok_done + r, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
@@ -507,7 +524,9 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
             in_local += h->lo_of[h->root] * row_bytes;
         } else {
             if (k >= 2) DH_CUDA(cudaStreamWaitEvent(h->s_in, h->ev_consumed[slot], 0));
+            trace_mark(h->s_in);   // 1: slot free
             DH_NCCL(nccl().Send(tok_ready, sizeof(uint32_t), ncclInt8, h->root, h->comm_in, h->s_in));
+            trace_mark(h->s_in);   // 2: ready token sent
             DH_NCCL(nccl().Recv(tok_done, sizeof(uint32_t), ncclInt8, h->root, h->comm_in, h->s_in));
             in_local = static_cast<const char*>(h->d_slot[slot]);
         }
@@ -529,6 +548,7 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
         }
     }
     DH_CUDA(cudaEventRecord(h->ev_scattered, h->s_in));
+    while (tracing && h->trace.size() % 6 != 4 && h->trace.size() < 6 * 64) trace_mark(h->s_in);   // ..3: scatter phase done
 
     // ---- the pipe of this rank's channels (stream s_cmp orders the input, kernels on the pipe's own streams) -------
     // the root's own rows are already in place: its kernels only wait for the caller's stream, not for the scatter
@@ -542,6 +562,13 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
     if (rc != DH_OK) return rc;
     rc = dh_pipe_input_event(h->pipe, h->ev_consumed[slot]);
     if (rc != DH_OK) return rc;
+    if (tracing && h->trace.size() % 6 == 4) {   // 4: first kernel has read the input (recorded like ev_consumed)
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) == cudaSuccess) {
+            dh_pipe_input_event(h->pipe, e);
+            h->trace.push_back(e);
+        }
+    }
     DH_CUDA(cudaEventRecord(h->ev_computed, h->s_cmp));
     DH_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_computed, 0));
     rc = dh_pipe_sync(h->pipe, h->s_out);   // asynchronous pipes: the decoder kernel runs on an internal stream
@@ -573,6 +600,7 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
         }
     }
     DH_CUDA(cudaEventRecord(h->ev_gathered[slot], h->s_out));
+    if (tracing && h->trace.size() % 6 == 5) trace_mark(h->s_out);   // 5: gathered
     h->submitted++;
     return DH_OK;
 }
@@ -657,6 +685,14 @@ void dh_shard_destroy(dh_shard* h) {
     {
         dh::DeviceGuard guard(h->device);
         cudaDeviceSynchronize();
+        for (size_t k = 0; k + 6 <= h->trace.size(); k += 6) {
+            float t[6];
+            for (int j = 0; j < 6; j++) cudaEventElapsedTime(&t[j], h->trace[0], h->trace[k + j]);
+            fprintf(stderr, "[shard trace] rank %d step %2zu: scatter %8.3f | %8.3f | %8.3f | %8.3f  input read %8.3f  gathered %8.3f ms\n",
+                    h->rank, k / 6, t[0], t[1], t[2], t[3], t[4], t[5]);
+        }
+        for (cudaEvent_t e : h->trace) cudaEventDestroy(e);
+        h->trace.clear();
         if (h->comm_out && nccl().ok) nccl().CommDestroy(h->comm_out);
     }
     dh_pipe_destroy(h->pipe);
