@@ -230,3 +230,35 @@ def test_shard_world1_other_protocols(name, s16):
             bad = shard.ShardedPipe(C, dh_proto, max_chunk=n, device="cuda:0", fmt=dh.FMT_S16)
             blk = torch.zeros((C, bad.pitch), dtype=torch.int16, device="cuda")
             bad.submit(blk, n, scatter=True)
+
+
+def test_shard_api_misuse_is_reported():
+    """Error behaviour of dh_shard_*: return codes + dh_last_error, no crash, the object stays usable."""
+    import digiham_b200 as dh
+    from digiham_b200 import shard
+    C, n = 8, 4000
+    sp = shard.ShardedPipe(C, dh.PROTO_DMR, max_chunk=n, device="cuda:0")
+    assert sp.scatter_path == 0
+    blk = torch.zeros((C, sp.pitch), dtype=torch.float32, device="cuda")
+    with pytest.raises(dh.DhError):
+        sp.collect_step()                                   # nothing in flight
+    with pytest.raises(dh.DhError):
+        sp.submit(torch.zeros((C, sp.pitch + 4), dtype=torch.float32, device="cuda"), n)   # wrong pitch
+    with pytest.raises(dh.DhError):
+        sp.submit(blk, n + 1)                               # beyond max_chunk
+    sp.submit(blk, n)
+    sp.submit(blk, n)
+    with pytest.raises(dh.DhError):
+        sp.submit(blk, n)                                   # two steps already in flight
+    sp.collect_step()
+    sp.discard_step()
+    with pytest.raises(dh.DhError):
+        sp.output(C)                                        # channel out of range
+    assert sp.output(0) == b"" and sp.meta(C - 1) == b""     # silence decodes to nothing
+    sp.submit(blk, n)
+    sp.collect_step()
+    sp.close()
+    with pytest.raises(dh.DhError):
+        shard.ShardedPipe(0, dh.PROTO_DMR, max_chunk=n, device="cuda:0")     # fewer channels than ranks
+    with pytest.raises(dh.DhError):
+        shard.ShardedPipe(C, 99, max_chunk=n, device="cuda:0")               # unknown protocol
