@@ -76,7 +76,7 @@ def test_shard_world1_pack_and_sink(s16):
     sp.close()
 
 
-def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False):
+def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False, root=0):
     if no_ipc:
         os.environ["DH_SHARD_NO_IPC"] = "1"
     else:
@@ -90,12 +90,13 @@ def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False):
     dev = torch.device("cuda", rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     try:
-        sp = shard.ShardedPipe(channels, dh.PROTO_DMR, max_chunk=n, device=dev, fmt=dh.FMT_S16 if s16 else dh.FMT_F32)
+        sp = shard.ShardedPipe(channels, dh.PROTO_DMR, max_chunk=n, device=dev, fmt=dh.FMT_S16 if s16 else dh.FMT_F32,
+                               root=root)
         data = ref_in = None
-        if rank == 0:
+        if rank == root:
             data, ref_in = _make_input(channels, n, steps, seed=43, s16=s16, device=dev)
         _run_sharded(sp, data, n, steps, sp.pitch, scatter=True)
-        if rank == 0:
+        if rank == root:
             orc = oracle_lib.best()
             _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, ref_in, threads=8, chunk=4096)
             bad = [c for c in range(channels)
@@ -110,7 +111,7 @@ def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False):
         # the streams continue: the oracle sees phase-1 samples of these channels followed by the local ones
         gathered = [None] * world
         dist.all_gather_object(gathered, local_ref)
-        if rank == 0:
+        if rank == root:
             full2 = np.concatenate(gathered, axis=0)
             _, outs2, metas2 = orc.pipe_batch(oracle_lib.PROTO_DMR, np.concatenate([ref_in, full2], axis=1), threads=8,
                                               chunk=4096)
@@ -148,6 +149,25 @@ def test_shard_two_ranks_scatter_compute_gather(s16, no_ipc):
     assert path == (1 if no_ipc else 2), "scatter path %d" % path
     status2, _, _ = q.get(timeout=10)
     assert status2 == "ok"
+
+
+def test_shard_two_ranks_root_is_not_rank_zero():
+    """The ingest / gathering rank may be any rank (here rank 1 of 2)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 33, 12000, 3, True, q, False, 1)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=300)
+        assert p.exitcode == 0
+    status, nbytes, nlocal, path = q.get(timeout=10)
+    assert status == "ok" and nbytes > 0 and nlocal == 16 and path == 2
+    assert q.get(timeout=10)[0] == "ok"
 
 
 def _cpp_host(tmp_path, world):
