@@ -343,6 +343,7 @@ def sharded_arm(args, dh, dist, dev, rank, world, stream, barrier, max_over_rank
         torch.cuda.synchronize()
         dt = max_over_ranks(time.perf_counter() - t0)
         launches, wire_bytes, _ = sp.stats()
+        out["gather_path" + ("" if fmt_name == "f32" else "_s16")] = {1: "nccl send/recv", 2: "pack kernel stores -> CUDA IPC root buffer"}.get(sp.gather_path, "none")
         out["scatter_path" + ("" if fmt_name == "f32" else "_s16")] = {1: "nccl send/recv", 2: "copy engines -> CUDA IPC peer slots"}.get(sp.scatter_path, "none")
         esz = 2 if fmt == dh.FMT_S16 else 4
         scatter_bytes = (world - 1) * Cs * pitch * esz

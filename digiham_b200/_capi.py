@@ -150,6 +150,7 @@ def lib():
     L.dh_shard_meta.argtypes = [ctypes.c_void_p, ctypes.c_uint64, c_void_pp, ctypes.POINTER(ctypes.c_size_t)]
     L.dh_shard_clear.argtypes = [ctypes.c_void_p]
     L.dh_shard_scatter_path.argtypes = [ctypes.c_void_p]
+    L.dh_shard_gather_path.argtypes = [ctypes.c_void_p]
     L.dh_shard_stats.argtypes = [ctypes.c_void_p, c_u64_p, c_u64_p, c_u64_p]
     L.dh_shard_destroy.argtypes = [ctypes.c_void_p]
     L.dh_shard_destroy.restype = None

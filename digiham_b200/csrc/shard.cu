@@ -171,11 +171,15 @@ struct dh_shard {
     // scatter through peer memory: the root's views of every peer's two slots (cudaIpcOpenMemHandle), one copy stream
     // per peer so that the copy engines work on all peers at once, and the 4-byte NCCL tokens that order the copies
     bool ipc_scatter = false;
+    // gather through peer memory: the peers' views of the root's two wire buffers; their pack kernel stores its wire
+    // block straight into the root's memory over NVLink (pack + gather in one kernel), NCCL carries two tokens
+    bool ipc_gather = false;
+    void* root_wire[2] = {nullptr, nullptr};
     std::vector<void*> peer_slot[2];
     std::vector<cudaStream_t> s_peer;
     std::vector<cudaEvent_t> ev_peer;
     cudaEvent_t ev_ready = nullptr;
-    uint32_t* d_token = nullptr;                    // [2 * world] scratch for the tokens
+    uint32_t* d_token = nullptr;                    // [4 * world] scratch for the tokens (scatter: first half, gather: second)
     std::vector<cudaEvent_t> trace;                 // diagnostics (DH_SHARD_TRACE): 6 timing events per step
     cudaEvent_t ev_user = nullptr, ev_scattered = nullptr, ev_computed = nullptr, ev_join = nullptr;
     cudaEvent_t ev_consumed[2] = {nullptr, nullptr};   // first kernel of the step has read its input block
@@ -199,8 +203,8 @@ namespace {
 int setup_ipc_scatter(dh_shard* h) {
     const int world = h->world, rank = h->rank, root = h->root;
     const bool is_root = rank == root;
-    DH_CUDA(cudaMalloc(&h->d_token, 2 * (size_t) world * sizeof(uint32_t)));
-    DH_CUDA(cudaMemset(h->d_token, 0, 2 * (size_t) world * sizeof(uint32_t)));
+    DH_CUDA(cudaMalloc(&h->d_token, 4 * (size_t) world * sizeof(uint32_t)));
+    DH_CUDA(cudaMemset(h->d_token, 0, 4 * (size_t) world * sizeof(uint32_t)));
     DH_CUDA(cudaEventCreateWithFlags(&h->ev_ready, cudaEventDisableTiming));
     struct Handles {
         cudaIpcMemHandle_t slot[2];
@@ -223,10 +227,33 @@ int setup_ipc_scatter(dh_shard* h) {
         }
         DH_CUDA(cudaMemcpyAsync(d_handles + rank, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->s_in));
         DH_NCCL(nccl().Send(d_handles + rank, sizeof(Handles), ncclInt8, root, h->comm_in, h->s_in));
-        // the root's verdict
-        DH_NCCL(nccl().Recv(h->d_token, sizeof(uint32_t), ncclInt8, root, h->comm_in, h->s_in));
-        DH_CUDA(cudaMemcpyAsync(&usable, h->d_token, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_in));
+        // the root's verdict on the scatter + the handles of its two wire buffers (ok = may be used for the gather)
+        Handles theirs;
+        DH_NCCL(nccl().Recv(d_handles + root, sizeof(Handles), ncclInt8, root, h->comm_in, h->s_in));
+        DH_CUDA(cudaMemcpyAsync(&theirs, d_handles + root, sizeof(Handles), cudaMemcpyDeviceToHost, h->s_in));
         DH_CUDA(cudaStreamSynchronize(h->s_in));
+        usable = theirs.pad[0];
+        uint32_t gather_ok = theirs.ok;
+        for (int i = 0; i < 2 && gather_ok; i++) {
+            if (cudaIpcOpenMemHandle(&h->root_wire[i], theirs.slot[i], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                h->root_wire[i] = nullptr;
+                gather_ok = 0;
+            }
+        }
+        // every peer reports, the root answers with the common decision
+        DH_CUDA(cudaMemcpyAsync(h->d_token + 1, &gather_ok, sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_in));
+        DH_NCCL(nccl().Send(h->d_token + 1, sizeof(uint32_t), ncclInt8, root, h->comm_in, h->s_in));
+        DH_NCCL(nccl().Recv(h->d_token + 1, sizeof(uint32_t), ncclInt8, root, h->comm_in, h->s_in));
+        DH_CUDA(cudaMemcpyAsync(&gather_ok, h->d_token + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, h->s_in));
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+        if (!gather_ok) {
+            for (int i = 0; i < 2; i++) {
+                if (h->root_wire[i]) cudaIpcCloseMemHandle(h->root_wire[i]);
+                h->root_wire[i] = nullptr;
+            }
+        }
+        h->ipc_gather = gather_ok != 0;
     } else {
         DH_NCCL(nccl().GroupStart());
         for (int r = 0; r < world; r++)
@@ -255,11 +282,42 @@ int setup_ipc_scatter(dh_shard* h) {
                 DH_CUDA(cudaEventCreateWithFlags(&h->ev_peer[r], cudaEventDisableTiming));
             }
         }
-        DH_CUDA(cudaMemcpyAsync(h->d_token, &usable, sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_in));
+        // the root's own wire buffers for the gather direction
+        Handles mine;
+        std::memset(&mine, 0, sizeof(mine));
+        mine.ok = (getenv("DH_SHARD_NO_IPC") || getenv("DH_SHARD_NO_IPC_GATHER")) ? 0u : 1u;
+        for (int i = 0; i < 2 && mine.ok; i++) {
+            if (cudaIpcGetMemHandle(&mine.slot[i], h->d_wire[i]) != cudaSuccess) {
+                cudaGetLastError();
+                mine.ok = 0;
+            }
+        }
+        mine.pad[0] = usable;   // the verdict on the scatter travels in the same message
+        DH_CUDA(cudaMemcpyAsync(d_handles + root, &mine, sizeof(mine), cudaMemcpyHostToDevice, h->s_in));
         DH_NCCL(nccl().GroupStart());
         for (int r = 0; r < world; r++)
-            if (r != root) DH_NCCL(nccl().Send(h->d_token, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+            if (r != root) DH_NCCL(nccl().Send(d_handles + root, sizeof(Handles), ncclInt8, r, h->comm_in, h->s_in));
         DH_NCCL(nccl().GroupEnd());
+        // collect the peers' reports on the gather mapping, answer with the common decision
+        DH_NCCL(nccl().GroupStart());
+        for (int r = 0; r < world; r++)
+            if (r != root) DH_NCCL(nccl().Recv(h->d_token + world + r, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+        DH_NCCL(nccl().GroupEnd());
+        std::vector<uint32_t> reports((size_t) world, 1);
+        DH_CUDA(cudaMemcpyAsync(reports.data(), h->d_token + world, (size_t) world * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                h->s_in));
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+        uint32_t gather_ok = mine.ok;
+        for (int r = 0; r < world; r++)
+            if (r != root && !reports[r]) gather_ok = 0;
+        DH_CUDA(cudaMemcpyAsync(h->d_token + 1, &gather_ok, sizeof(uint32_t), cudaMemcpyHostToDevice, h->s_in));
+        DH_NCCL(nccl().GroupStart());
+        for (int r = 0; r < world; r++)
+            if (r != root) DH_NCCL(nccl().Send(h->d_token + 1, sizeof(uint32_t), ncclInt8, r, h->comm_in, h->s_in));
+        DH_NCCL(nccl().GroupEnd());
+        DH_CUDA(cudaStreamSynchronize(h->s_in));
+        h->ipc_gather = gather_ok != 0;
+        DH_CUDA(cudaMemsetAsync(h->d_token, 0, 4 * (size_t) world * sizeof(uint32_t), h->s_in));
         DH_CUDA(cudaStreamSynchronize(h->s_in));
     }
     cudaFree(d_handles);
@@ -570,15 +628,33 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
         }
     }
     DH_CUDA(cudaEventRecord(h->ev_computed, h->s_cmp));
-    DH_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_computed, 0));
-    rc = dh_pipe_sync(h->pipe, h->s_out);   // asynchronous pipes: the decoder kernel runs on an internal stream
-    if (rc != DH_OK) return rc;
 
     // ---- pack + gather (stream s_out, communicator comm_out) -------------------------------------------------------
     dh::DecoderView view;
     rc = dh::decoder_view(h->dec, slot, &view);
     if (rc != DH_OK) return rc;
-    uint8_t* my_wire = is_root ? h->d_wire[slot] + h->region_off[h->rank] : h->d_wire[slot];
+    const bool fused_gather = h->ipc_gather && h->world > 1;
+    uint32_t* tok_free = h->d_token + 2 * h->world;   // gather tokens live behind the scatter tokens
+    uint32_t* tok_packed = h->d_token + 3 * h->world;
+    // Fused form: the root first tells every peer that wire buffer `slot` is free again (its host has read or dropped
+    // the step that used it, and the stream has passed that step's gather), a peer's pack kernel then stores its block
+    // straight into the root's buffer over NVLink and a second token reports it.  The peers post the receive of the
+    // "free" token before they wait for their kernels, so the root's send never spins for long.
+    if (fused_gather) {
+        if (is_root) {
+            DH_NCCL(nccl().GroupStart());
+            for (int r = 0; r < h->world; r++)
+                if (r != h->root) DH_NCCL(nccl().Send(tok_free + r, sizeof(uint32_t), ncclInt8, r, h->comm_out, h->s_out));
+            DH_NCCL(nccl().GroupEnd());
+        } else {
+            DH_NCCL(nccl().Recv(tok_free, sizeof(uint32_t), ncclInt8, h->root, h->comm_out, h->s_out));
+        }
+    }
+    DH_CUDA(cudaStreamWaitEvent(h->s_out, h->ev_computed, 0));
+    rc = dh_pipe_sync(h->pipe, h->s_out);   // asynchronous pipes: the decoder kernel runs on an internal stream
+    if (rc != DH_OK) return rc;
+    uint8_t* my_wire = is_root ? h->d_wire[slot] + h->region_off[h->rank]
+                               : (fused_gather ? static_cast<uint8_t*>(h->root_wire[slot]) + h->region_off[h->rank] : h->d_wire[slot]);
     const unsigned blocks = (h->n_local + 3) / 4 < 148u * 8u ? (h->n_local + 3) / 4 : 148u * 8u;
     pack_results_kernel<<<blocks, 128, 0, h->s_out>>>(view.counts, view.out, view.out_cap, view.ev, view.ev_cap, my_wire,
                                                        h->n_local, h->wire.w_out, h->wire.w_ev,
@@ -591,10 +667,15 @@ int dh_shard_submit_device(dh_shard* h, const void* d_in, size_t pitch, size_t n
             DH_NCCL(nccl().GroupStart());
             for (int r = 0; r < h->world; r++) {
                 if (r == h->root) continue;
-                DH_NCCL(nccl().Recv(h->d_wire[slot] + h->region_off[r], h->wire.bytes(h->n_of[r]), ncclInt8, r,
-                                    h->comm_out, h->s_out));
+                if (fused_gather)
+                    DH_NCCL(nccl().Recv(tok_packed + r, sizeof(uint32_t), ncclInt8, r, h->comm_out, h->s_out));
+                else
+                    DH_NCCL(nccl().Recv(h->d_wire[slot] + h->region_off[r], h->wire.bytes(h->n_of[r]), ncclInt8, r,
+                                        h->comm_out, h->s_out));
             }
             DH_NCCL(nccl().GroupEnd());
+        } else if (fused_gather) {
+            DH_NCCL(nccl().Send(tok_packed, sizeof(uint32_t), ncclInt8, h->root, h->comm_out, h->s_out));
         } else {
             DH_NCCL(nccl().Send(my_wire, h->wire.bytes(h->n_local), ncclInt8, h->root, h->comm_out, h->s_out));
         }
@@ -672,6 +753,8 @@ int dh_shard_clear(dh_shard* h) {
 
 int dh_shard_scatter_path(const dh_shard* h) { return h ? (h->world > 1 ? (h->ipc_scatter ? 2 : 1) : 0) : 0; }
 
+int dh_shard_gather_path(const dh_shard* h) { return h ? (h->world > 1 ? (h->ipc_gather ? 2 : 1) : 0) : 0; }
+
 int dh_shard_stats(dh_shard* h, uint64_t* launches, uint64_t* wire_bytes_per_step, uint64_t* d2h_bytes) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_shard_stats: handle is NULL");
     if (launches) *launches = dh_pipe_launch_count(h->pipe) + h->packs;
@@ -701,6 +784,8 @@ void dh_shard_destroy(dh_shard* h) {
         for (int i = 0; i < 2; i++)
             for (void* p : h->peer_slot[i])
                 if (p) cudaIpcCloseMemHandle(p);
+        for (int i = 0; i < 2; i++)
+            if (h->root_wire[i]) cudaIpcCloseMemHandle(h->root_wire[i]);
         for (cudaStream_t s : h->s_peer)
             if (s) cudaStreamDestroy(s);
         for (cudaEvent_t e : h->ev_peer)

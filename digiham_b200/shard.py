@@ -132,6 +132,11 @@ class ShardedPipe:
         """0 = single rank, 1 = NCCL send / recv, 2 = copy engines into IPC-mapped peer slots."""
         return lib().dh_shard_scatter_path(self._h)
 
+    @property
+    def gather_path(self):
+        """0 = single rank, 1 = NCCL send / recv, 2 = pack kernel stores into the root's IPC-mapped wire buffer."""
+        return lib().dh_shard_gather_path(self._h)
+
     def stats(self):
         """(kernels launched by this rank, bytes of its wire block per step, bytes read back on the root)."""
         a, b, c = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()

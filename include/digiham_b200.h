@@ -333,8 +333,9 @@ DH_API int dh_pipe_state_import(dh_pipe* h, const void* h_buf, size_t bytes, voi
  *   scatter  the root (ingest) rank holds the block of ALL channels, every peer receives its rows — written into
  *            the peers' input slots by the root's copy engines over NVLink (slots mapped through CUDA IPC, NCCL
  *            only carries 4-byte ordering tokens), or sent with ncclSend / ncclRecv when that mapping is unavailable;
- *   gather   every rank packs its decoder results of the step (frames, metadata events, counts) into one wire block
- *            and sends it to the root, which exposes all channels through dh_shard_output / dh_shard_meta.
+ *   gather   every rank packs its decoder results of the step (frames, metadata events, counts) into one wire block —
+ *            stored by the pack kernel directly into the root's memory over NVLink (CUDA IPC), or sent with
+ *            ncclSend / ncclRecv — and the root exposes all channels through dh_shard_output / dh_shard_meta.
  * Steps are pipelined: scatter of step k+1, the kernels of step k and the gather of step k-1 overlap (three streams,
  * two communicators); up to two steps may be in flight.  Every call below is COLLECTIVE: all ranks make the same
  * sequence of create / submit / collect / discard calls with the same n and flags.
@@ -384,6 +385,10 @@ DH_API int dh_shard_clear(dh_shard* h);
 /* how the rows travel in a scattering submit: 0 = single rank, 1 = NCCL send / recv, 2 = the root's copy engines write
  * into the peers' input slots mapped through CUDA IPC (chosen at create; DH_SHARD_NO_IPC=1 in the environment forces 1) */
 DH_API int dh_shard_scatter_path(const dh_shard* h);
+/* how the wire blocks travel to the root: 0 = single rank, 1 = ncclSend / ncclRecv, 2 = every peer's pack kernel stores
+ * its block straight into the root's wire buffer mapped through CUDA IPC (pack + gather in one kernel, NCCL carries two
+ * 4-byte tokens per peer and step); DH_SHARD_NO_IPC=1 or DH_SHARD_NO_IPC_GATHER=1 force 1 */
+DH_API int dh_shard_gather_path(const dh_shard* h);
 /* kernels launched by this rank (pipe + pack), bytes of its wire block per step, bytes read back by collect (root) */
 DH_API int dh_shard_stats(dh_shard* h, uint64_t* launches, uint64_t* wire_bytes_per_step, uint64_t* d2h_bytes);
 DH_API void dh_shard_destroy(dh_shard* h);

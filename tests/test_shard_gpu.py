@@ -101,7 +101,8 @@ def _worker(rank, world, port, channels, n, steps, s16, q, no_ipc=False, root=0)
             _, outs, metas = orc.pipe_batch(oracle_lib.PROTO_DMR, ref_in, threads=8, chunk=4096)
             bad = [c for c in range(channels)
                    if sp.output(c) != outs[c].tobytes() or sp.meta(c) != metas[c]]
-            q.put(("ok" if not bad else "mismatch %s" % bad[:8], sum(len(o) for o in outs), sp.hi - sp.lo, sp.scatter_path))
+            q.put(("ok" if not bad else "mismatch %s" % bad[:8], sum(len(o) for o in outs), sp.hi - sp.lo,
+                   sp.scatter_path * 10 + sp.gather_path))
         # second phase on the same object: every rank feeds its own rows (no scatter), results still gathered
         sp.clear()
         lo, hi = sp.lo, sp.hi
@@ -146,7 +147,7 @@ def test_shard_two_ranks_scatter_compute_gather(s16, no_ipc):
         assert p.exitcode == 0
     status, nbytes, nlocal, path = q.get(timeout=10)
     assert status == "ok" and nbytes > 27 * 50 and nlocal == 51
-    assert path == (1 if no_ipc else 2), "scatter path %d" % path
+    assert path == (11 if no_ipc else 22), "scatter / gather paths %d" % path
     status2, _, _ = q.get(timeout=10)
     assert status2 == "ok"
 
@@ -166,7 +167,7 @@ def test_shard_two_ranks_root_is_not_rank_zero():
         p.join(timeout=300)
         assert p.exitcode == 0
     status, nbytes, nlocal, path = q.get(timeout=10)
-    assert status == "ok" and nbytes > 0 and nlocal == 16 and path == 2
+    assert status == "ok" and nbytes > 0 and nlocal == 16 and path == 22
     assert q.get(timeout=10)[0] == "ok"
 
 
