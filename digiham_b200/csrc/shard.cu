@@ -9,8 +9,11 @@
 //            NCCL only carries the two 4-byte tokens per peer and step that order them ("slot free" / "rows landed");
 //            grouped ncclSend / ncclRecv of the rows themselves is the fallback when the slots cannot be mapped;
 //   gather   every rank packs the decoder results of the step — fixed-slot byte rows, 16-byte metadata event records,
-//            per-channel counts — into one wire block, trimmed to the per-step slot widths, and sends it to the root,
-//            which feeds all of them through one host-side result sink (result_sink.cu) in global channel order.
+//            per-channel counts — into one wire block with per-step slot widths; on a peer the pack kernel stores the
+//            block straight into the root's wire buffer (mapped through CUDA IPC: pack and gather are one kernel, only
+//            the used bytes cross NVLink), ordered by two 4-byte NCCL tokens; ncclSend / ncclRecv of the block is the
+//            fallback.  The root feeds all blocks through one host-side result sink (result_sink.cu) in global
+//            channel order.
 // The three phases of consecutive steps overlap: scatter(k+1) runs on its own stream and communicator while the
 // kernels of step k run (cross-step pipelined, dh_pipe_set_async) and the wire block of step k-1 travels on a third
 // stream over a second communicator (ncclCommSplit), so neither collective waits behind the other.  Input blocks,
