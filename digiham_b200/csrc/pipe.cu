@@ -389,7 +389,13 @@ int pipe_submit_host(dh_pipe* h, const void* h_in, size_t in_pitch, size_t n, bo
         h->stage_pitch = (h->max_chunk + 3) & ~(size_t) 3;
         DH_CUDA(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
         DH_CUDA(cudaStreamCreateWithFlags(&h->s_compute, cudaStreamNonBlocking));
-        DH_CUDA(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
+        {
+            // the read-back stream runs small kernels (row compaction, counter reset) that must not queue behind the FIR
+            // grid of the next step: highest priority
+            int lo_prio = 0, hi_prio = 0;
+            DH_CUDA(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+            DH_CUDA(cudaStreamCreateWithPriority(&h->s_back, cudaStreamNonBlocking, hi_prio));
+        }
         for (int i = 0; i < 2; i++) {
             DH_CUDA(cudaMalloc(&h->d_slot[i], (size_t) h->channels * h->stage_pitch * sizeof(float)));
             DH_CUDA(cudaMemset(h->d_slot[i], 0, (size_t) h->channels * h->stage_pitch * sizeof(float)));

@@ -466,7 +466,7 @@ int dh_shard_create(dh_shard** out, void* nccl_comm, int rank, int world, int ro
     DH_TRY(cudaStreamCreateWithPriority(&h->s_in, cudaStreamNonBlocking, hi_prio));
     DH_TRY(cudaStreamCreateWithFlags(&h->s_cmp, cudaStreamNonBlocking));
     DH_TRY(cudaStreamCreateWithPriority(&h->s_out, cudaStreamNonBlocking, hi_prio));
-    DH_TRY(cudaStreamCreateWithFlags(&h->s_back, cudaStreamNonBlocking));
+    DH_TRY(cudaStreamCreateWithPriority(&h->s_back, cudaStreamNonBlocking, hi_prio));   // read-back: compaction kernels + copies
     DH_TRY(cudaEventCreateWithFlags(&h->ev_user, cudaEventDisableTiming));
     DH_TRY(cudaEventCreateWithFlags(&h->ev_scattered, cudaEventDisableTiming));
     DH_TRY(cudaEventCreateWithFlags(&h->ev_computed, cudaEventDisableTiming));
