@@ -60,6 +60,10 @@ def lib():
     L.dh_demod_process.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_size_t,
                                    ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
     L.dh_demod_reset.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.dh_demod_set_split.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    L.dh_demod_kernels_per_call.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_demod.argtypes = [ctypes.c_void_p]
+    L.dh_pipe_demod.restype = ctypes.c_void_p
     L.dh_demod_destroy.argtypes = [ctypes.c_void_p]
     L.dh_demod_destroy.restype = None
     L.dh_decoder_create.argtypes = [c_void_pp, ctypes.c_int, ctypes.c_uint32, ctypes.c_int]
@@ -287,6 +291,14 @@ class DemodBank:
     def max_symbols(self, n):
         return lib().dh_demod_max_symbols(self._h, n)
 
+    def set_split(self, enable):
+        """dh_demod_set_split: one kernel (False) or search chain + per-symbol + per-block kernels (True)."""
+        check(lib().dh_demod_set_split(self._h, int(bool(enable))))
+
+    @property
+    def kernels_per_call(self):
+        return lib().dh_demod_kernels_per_call(self._h)
+
     def reserve(self, max_n):
         """Returns (device pointer, pitch) of the zero-copy input block."""
         ptr = ctypes.c_void_p()
@@ -440,6 +452,14 @@ class Pipe:
         self.decoder.proto = proto
         self.decoder.device = self.device
         self.decoder.close = lambda: None
+
+    def set_demod_split(self, enable):
+        """Schedule of the pipe's demodulator bank (dh_demod_set_split on dh_pipe_demod)."""
+        check(lib().dh_demod_set_split(ctypes.c_void_p(lib().dh_pipe_demod(self._h)), int(bool(enable))))
+
+    @property
+    def demod_kernels_per_call(self):
+        return lib().dh_demod_kernels_per_call(ctypes.c_void_p(lib().dh_pipe_demod(self._h)))
 
     @property
     def host_pitch(self):

@@ -38,6 +38,8 @@ constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (i
 // slower on B200 (0.42 vs 0.34 ms at 4096 channels: 342 CTAs are 1.15 waves of 2 x 148).
 constexpr int kThreads = 64;
 constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
+// dh_demod_set_split default of new banks (environment DH_DEMOD_SPLIT overrides it): see DESIGN.md, K2 split
+constexpr int kSplitDefault = 0;
 
 struct ChannelState {
     float vol_prev[kBlockSyms];  // volume ring content written by the previous block (zeros at power-on)
@@ -66,6 +68,14 @@ struct DemodParams {
     int carry_cap;
     int samples_cap;             // floats reserved per group for staged samples
     int group_floats;            // floats of shared memory per group
+    // split mode only (demod_search_kernel -> demod_volume_kernel -> demod_slice_kernel)
+    ChannelState* state_out;     // state the NEXT call reads (the two state sets alternate like the work rows)
+    int2* rec;                   // [channels][rec_pitch] {first window, pending nudge} of every block of this call
+    int4* hdr;                   // [channels] {full blocks, symbols of the trailing partial block, j_done at entry,
+                                 //             carry_len at entry}
+    float2* va;                  // [channels][rec_pitch * 100] {volume, average} of every symbol of this call
+    int rec_pitch;
+    int prefetch;                // search kernel: pull the next block's lines into L2 while the current one is searched
 };
 
 __device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
@@ -83,6 +93,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dh::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void prefetch_l2(const void* gmem) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -480,6 +493,374 @@ __global__ void __launch_bounds__(THREADS, MINB) demod_kernel(const __grid_const
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Split form of K2 (dh_demod_set_split).  The only sequential dependency of the demodulator is the +-1 nudge that the
+// variance search of block b hands to block b + 1; the window sums, the volume ring and the slicing of a block depend
+// on nothing but that block's position {P, nudge}.  So the chain is walked by a kernel that does nothing else
+// (demod_search_kernel: same lane groups and staging as demod_kernel, a third of its instructions per block), which
+// records {P, nudge} of every block; two wide kernels without any serial part finish the job:
+//   demod_volume_kernel  one lane per symbol: window sums -> {volume, average} (gfsk_demodulator.cpp:28-35, 82-83, 88)
+//   demod_slice_kernel   one 10-lane group per (channel, block): ring min / max = (prefix over this block's volumes) x
+//                        (suffix over the previous block's) by the same shuffle scans as demod_kernel, thresholds,
+//                        symbols (gfsk_demodulator.cpp:88-122)
+// Arithmetic, rounding and operation order are those of demod_kernel (the helpers are shared), only the schedule
+// differs.  The per-channel state alternates between two sets so that the slice group of block 0 can read the previous
+// call's volume ring while the group of the last full block already writes the next one.
+// ---------------------------------------------------------------------------------------------------------------------
+
+// the logical sample stream of one channel: carried tail (work row) followed by the chunk (same row, or the caller's)
+struct RowView {
+    const float* row0;      // &stream[0] inside the work row
+    const float* ext_row;   // &chunk[0] inside the caller's rows, or nullptr: the chunk follows the tail in the work row
+    int carry_len;
+    int col0;
+    int T;                  // samples visible to this call
+    __device__ __forceinline__ RowView(const DemodParams& p, int ch, int carry_len_) {
+        carry_len = carry_len_;
+        col0 = p.carry_cap - carry_len;
+        row0 = p.work + (size_t) ch * p.pitch + col0;
+        ext_row = p.ext ? p.ext + (size_t) ch * p.ext_pitch : nullptr;
+        T = carry_len + p.n;
+    }
+    __device__ __forceinline__ const float* at(int x) const {
+        return (ext_row != nullptr && x >= carry_len) ? ext_row + (x - carry_len) : row0 + x;
+    }
+    // offset of sample P inside its 16-byte unit (0 for a range that starts in the tail of an `ext` call: it is
+    // copied element by element because it may straddle two buffers)
+    __device__ __forceinline__ int align_of(int P) const {
+        if (ext_row == nullptr) return (col0 + P) & 3;
+        return P >= carry_len ? (P - carry_len) & 3 : 0;
+    }
+    // asynchronous staging of [P, P + len) by W cooperating lanes (this one is lane l of them) with aligned 16-byte
+    // copies; sample P + x lands at S[align_of(P) + x]
+    template <int W>
+    __device__ __forceinline__ void stage(float* S, int P, int len, int l) const {
+        const int a0 = align_of(P);
+        if (ext_row == nullptr) {
+            const float4* src = reinterpret_cast<const float4*>(row0 + P - a0);
+            float4* dst = reinterpret_cast<float4*>(S);
+            const int nvec = (a0 + len + 3) >> 2;
+            for (int v = l; v < nvec; v += W) cp_async16(dst + v, src + v);
+        } else if (P >= carry_len) {
+            // whole vectors as long as they end inside the caller's row, single samples behind them (never read
+            // past sample T - 1: the buffer is not ours)
+            const float* base = ext_row + (P - carry_len) - a0;
+            const int avail = T - P + a0;
+            const int want = a0 + len;
+            const int nvec = min(want, avail) >> 2;
+            const float4* src = reinterpret_cast<const float4*>(base);
+            float4* dst = reinterpret_cast<float4*>(S);
+            for (int v = l; v < nvec; v += W) cp_async16(dst + v, src + v);
+            for (int x = 4 * nvec + l; x < min(want, avail); x += W) cp_async4(S + x, base + x);
+        } else {
+            for (int x = l; x < len && P + x < T; x += W) cp_async4(S + x, at(P + x));
+        }
+        cp_async_commit();
+    }
+};
+
+// K2a: the nudge chain.  Lane groups, staging and the search itself are those of demod_kernel; per block it records
+// where the block starts and which nudge is pending, at the end it carries the unconsumed tail and the scalar state.
+template <int G, int SPS, int THREADS>
+__global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_constant__ DemodParams p) {
+    extern __shared__ __align__(16) float smem[];
+    constexpr int kPerWarp = Group<G>::kPerWarp;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp_in_warp = lane / G;
+    if (grp_in_warp >= kPerWarp) return;
+    const int gl = lane - grp_in_warp * G;
+    const int grp = warp * kPerWarp + grp_in_warp;
+    const int ch = blockIdx.x * ((THREADS / 32) * kPerWarp) + grp;
+    if (ch >= p.channels) return;
+    const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
+
+    const int sps = SPS > 0 ? SPS : p.sps;
+    float* S = smem + (size_t) grp * p.group_floats;
+    double* var = reinterpret_cast<double*>(S + p.samples_cap);
+
+    const ChannelState* st = p.state + ch;
+    int vo = st->vo;
+    const int j_done_in = st->j_done;
+    const int carry_len = st->carry_len;
+    const RowView view(p, ch, carry_len);
+    const int T = view.T;
+    int2* rec = p.rec + (size_t) ch * p.rec_pitch;
+    const int full_len = kBlockSyms * sps + 2;   // what demod_kernel stages for a complete block
+
+    int P = 0;
+    int nfull = 0;
+    int m = processable(T, P, vo, sps);
+    if (gl == 0) rec[0] = make_int2(P, vo);
+    if (m == kBlockSyms) {
+        view.stage<G>(S, P, full_len, gl);
+        cp_async_wait_all();
+        __syncwarp(gmask);
+    }
+    while (m == kBlockSyms) {
+        const int a0 = view.align_of(P);
+        // where the next block starts does not depend on the search result: pull its 128-byte lines towards L2 now,
+        // so that the staging copies issued right after the search do not wait for DRAM
+        if (p.prefetch) {
+            const int Pn = P + kBlockSyms * sps + vo;
+            const int end = min(Pn + full_len, T);
+            if (end > Pn && (view.ext_row == nullptr || Pn >= carry_len)) {
+                for (int x = Pn + gl * 32; x < end + 31; x += G * 32) prefetch_l2(view.at(min(x, end - 1)));
+            }
+        }
+        // variance-minimum phase search over the 100 windows of the block (gfsk_demodulator.cpp:41-80)
+        for (int i = gl; i < sps; i += G) {
+            const float* w0 = S + a0 + i;
+            const float* wv = w0 + vo;          // windows 1..99 are shifted by the pending nudge
+            float total = __fadd_rn(0.0f, w0[0]);
+            if (SPS > 0) {
+#pragma unroll 11
+                for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * SPS]);
+            } else {
+                for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * sps]);
+            }
+            const double mean = (double) (SPS > 0 ? div_by_const(total, 1.0 / 100.0) : __fdiv_rn(total, 100.0f));
+            double d = __dsub_rn(mean, (double) w0[0]);
+            double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
+            if (SPS > 0) {
+#pragma unroll 11
+                for (int k = 1; k < kBlockSyms; k++) {
+                    d = __dsub_rn(mean, (double) wv[k * SPS]);
+                    dsum = __dadd_rn(dsum, __dmul_rn(d, d));
+                }
+            } else {
+                for (int k = 1; k < kBlockSyms; k++) {
+                    d = __dsub_rn(mean, (double) wv[k * sps]);
+                    dsum = __dadd_rn(dsum, __dmul_rn(d, d));
+                }
+            }
+            var[i] = __ddiv_rn(dsum, 100.0);
+        }
+        __syncwarp(gmask);
+        double vmin = var[0];
+        int vpos = 0;
+        for (int i = 1; i < sps; i++) {
+            const double v = var[i];
+            if (v < vmin) {
+                vmin = v;
+                vpos = i;
+            }
+        }
+        int vo_next = 0;
+        if (vmin <= 0 || vmin > 5000000) {
+            // no decision
+        } else if (vpos > 0 && vpos < sps / 2) {
+            vo_next = +1;
+        } else if (vpos >= sps / 2 && vpos < sps - 1) {
+            vo_next = -1;
+        }
+        const int P_next = P + kBlockSyms * sps + vo;
+        const int m_next = processable(T, P_next, vo_next, sps);
+        __syncwarp(gmask);   // every lane of the group is done with the staged block and with var[]
+        if (m_next == kBlockSyms) view.stage<G>(S, P_next, full_len, gl);
+        nfull++;
+        P = P_next;
+        vo = vo_next;
+        m = m_next;
+        if (gl == 0 && nfull < p.rec_pitch) rec[nfull] = make_int2(P, vo);
+        cp_async_wait_all();
+        __syncwarp(gmask);
+    }
+
+    // block `nfull` is incomplete (m < 100 symbols, possibly none): its windows are recomputed by the next call from
+    // the carried tail [P, T), written right-aligned in front of column carry_cap of the rows the NEXT call reads
+    const int keep = T - P;
+    {
+        float* dst = p.work_next + (size_t) ch * p.pitch + p.carry_cap - keep;
+        __syncwarp(gmask);
+        for (int idx = gl; idx < keep; idx += G) cp_async4(S + idx, view.at(P + idx));
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncwarp(gmask);
+        for (int idx = gl; idx < keep; idx += G) dst[idx] = S[idx];
+    }
+    if (gl == 0) {
+        const int j_cur = nfull == 0 ? j_done_in : 0;   // symbols of block `nfull` emitted by earlier calls
+        ChannelState* so = p.state_out + ch;
+        so->vo = vo;
+        so->j_done = m > j_cur ? m : j_cur;
+        so->carry_len = keep;
+        p.hdr[ch] = make_int4(nfull, m, j_done_in, carry_len);
+        const int emitted = nfull == 0 ? (m > j_done_in ? m - j_done_in : 0)
+                                       : (kBlockSyms - j_done_in) + (nfull - 1) * kBlockSyms + m;
+        p.nsym[ch] = (uint32_t) emitted;
+    }
+}
+
+// K2b: one lane per symbol.  Symbols are numbered b * 100 + j over the blocks of this call; a warp stages the (contiguous)
+// sample range its 32 windows cover and every lane sums its own window in the reference's order.
+constexpr int kVolThreads = 256;
+__host__ __device__ constexpr int vol_warp_floats(int sps) { return (32 * sps + 2 + 3 + 3 + 3) & ~3; }
+
+template <int SPS>
+__global__ void __launch_bounds__(kVolThreads) demod_volume_kernel(const __grid_constant__ DemodParams p) {
+    extern __shared__ __align__(16) float smem[];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int ch = blockIdx.x;
+    const int sps = SPS > 0 ? SPS : p.sps;
+    const int4 hd = p.hdr[ch];
+    const int total = hd.x * kBlockSyms + hd.y;   // symbols that have a complete window in this call
+    const int s0 = (blockIdx.y * (kVolThreads / 32) + warp) * 32;
+    if (s0 >= total) return;                      // warp-uniform
+    const int s = s0 + lane;
+    const bool active = s < total;
+    const int b = s / kBlockSyms;
+    const int j = s - b * kBlockSyms;
+    int start = 0;
+    if (active) {
+        const int2 r = p.rec[(size_t) ch * p.rec_pitch + b];
+        start = r.x + j * sps + (j ? r.y : 0);    // windows 1..99 of a block are shifted by its pending nudge
+    }
+    // window starts grow with the symbol number (also across blocks: P of block b + 1 is where window 99 of block b
+    // ends), so the warp's windows cover [start of lane 0, start of the last active lane + sps)
+    const int nact = min(32, total - s0);
+    const int lo = __shfl_sync(0xffffffffu, start, 0);
+    const int hi = __shfl_sync(0xffffffffu, start, nact - 1) + sps;
+    const RowView view(p, ch, hd.w);
+    float* S = smem + (size_t) warp * vol_warp_floats(sps);
+    const int a0 = view.align_of(lo);
+    view.stage<32>(S, lo, hi - lo, lane);
+    cp_async_wait_all();
+    __syncwarp();
+    if (!active) return;
+
+    const float* w = S + a0 + (start - lo);
+    float sum = 0.0f, vsum = 0.0f, vol, avg;
+    if (SPS > 0) {
+        constexpr int kLo = eval_lo(SPS > 0 ? SPS : 10), kHi = eval_hi(SPS > 0 ? SPS : 10);
+#pragma unroll
+        for (int i = 0; i < SPS; i++) {
+            const float v = w[i];
+            if (i >= kLo && i < kHi) sum = __fadd_rn(sum, v);
+            vsum = __fadd_rn(vsum, v);
+        }
+        vol = div_by_const(vsum, 1.0 / (double) (SPS > 0 ? SPS : 1));
+        avg = kHi - kLo == 4 ? __fmul_rn(sum, 0.25f) : div_by_const(sum, 1.0 / (double) (kHi - kLo));
+    } else {
+        for (int i = 0; i < sps; i++) {
+            const float v = w[i];
+            if (i >= p.lo && i < p.hi) sum = __fadd_rn(sum, v);
+            vsum = __fadd_rn(vsum, v);
+        }
+        vol = __fdiv_rn(vsum, (float) sps);
+        avg = __fdiv_rn(sum, (float) (p.hi - p.lo));
+    }
+    p.va[(size_t) ch * p.rec_pitch * kBlockSyms + s] = make_float2(vol, avg);
+}
+
+// K2c: calibrateAudio + slicing of one block per 10-lane group (three groups per warp), lane gl owns the symbols
+// [10 gl, 10 gl + 10) like in demod_kernel<10, ...>.
+constexpr int kSliceG = 10;
+__global__ void __launch_bounds__(kThreads) demod_slice_kernel(const __grid_constant__ DemodParams p) {
+    constexpr int G = kSliceG;
+    constexpr int kPerWarp = Group<G>::kPerWarp;
+    constexpr int CH = Group<G>::kChunk;
+    static_assert(CH * G == kBlockSyms && CH % 2 == 0, "the vector loads below assume 10 symbols per lane");
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int grp_in_warp = lane / G;
+    if (grp_in_warp >= kPerWarp) return;
+    const int gl = lane - grp_in_warp * G;
+    const int grp = warp * kPerWarp + grp_in_warp;
+    const int ch = blockIdx.x * ((kThreads / 32) * kPerWarp) + grp;
+    if (ch >= p.channels) return;
+    const unsigned gmask = ((1u << G) - 1u) << (grp_in_warp * G);
+
+    const int b = blockIdx.y;
+    const int4 hd = p.hdr[ch];
+    const int nfull = hd.x;
+    if (b > nfull) return;                                  // the whole group leaves together
+    const int m = b < nfull ? kBlockSyms : hd.y;            // symbols of this block that have a window
+    const int j_done_in = hd.z;
+    const int j_done = b == 0 ? j_done_in : 0;              // symbols of this block emitted by earlier calls
+    if (m <= j_done && nfull != 0) return;                  // nothing to emit and not in charge of the ring hand-over
+    const int j_first = gl * CH;
+
+    // {volume, average} of the own symbols; entries without a window (j >= m) were not written by this call
+    const float2* va = p.va + ((size_t) ch * p.rec_pitch + b) * kBlockSyms + j_first;
+    float volr[CH], avgr[CH], pv[CH], smn[CH], smx[CH];
+#pragma unroll
+    for (int q = 0; q < CH; q += 2) {
+        const float4 t = *reinterpret_cast<const float4*>(va + q);
+        volr[q] = j_first + q < m ? t.x : 0.0f;
+        avgr[q] = j_first + q < m ? t.y : 0.0f;
+        volr[q + 1] = j_first + q + 1 < m ? t.z : 0.0f;
+        avgr[q + 1] = j_first + q + 1 < m ? t.w : 0.0f;
+    }
+    // the ring content this block finds: the previous block's volumes (block 0: what the previous call left)
+    if (b == 0) {
+        const ChannelState* st = p.state + ch;
+#pragma unroll
+        for (int q = 0; q < CH; q++) pv[q] = st->vol_prev[j_first + q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < CH; q += 2) {
+            const float4 t = *reinterpret_cast<const float4*>(va - kBlockSyms + q);
+            pv[q] = t.x;
+            pv[q + 1] = t.z;
+        }
+    }
+    suffix_of_previous<G>(pv, smn, smx, gl, gmask);
+
+    float emn = FLT_MAX, emx = FLT_MIN;
+#pragma unroll
+    for (int q = 0; q < CH; q++) {
+        if (j_first + q < m) {
+            emn = min_lt(emn, volr[q]);
+            emx = max_gt(emx, volr[q]);
+        }
+    }
+    exclusive_up<G>(gmask, gl, emn, emx);
+
+    // calibrateAudio + slicing (gfsk_demodulator.cpp:88-104, 109-122); symbol j of block b is output number
+    // b * 100 + j - j_done_in of this call
+    float rmn = emn, rmx = emx;
+    uint8_t* const sym_out = p.sym + (size_t) ch * p.sym_pitch + (b * kBlockSyms - j_done_in + j_first);
+#pragma unroll
+    for (int q = 0; q < CH; q++) {
+        const int j = j_first + q;
+        if (j < m) {
+            rmn = min_lt(rmn, volr[q]);
+            rmx = max_gt(rmx, volr[q]);
+            if (j >= j_done) {
+                const float mn = min_lt(rmn, smn[q]);
+                const float mx = max_gt(rmx, smx[q]);
+                const float center = __fmul_rn(__fadd_rn(mx, mn), 0.5f);
+                const float a = avgr[q];
+                uint8_t s;
+                if (p.four_level) {
+                    const double c = (double) center;
+                    const float umid =
+                        __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mx, center), 0.625), c));
+                    const float lmid =
+                        __double2float_rn(__dadd_rn(__dmul_rn((double) __fsub_rn(mn, center), 0.625), c));
+                    s = a > center ? (a > umid ? 1 : 0) : (a < lmid ? 3 : 2);
+                } else {
+                    s = a > center ? (p.invert ? 0 : 1) : (p.invert ? 1 : 0);
+                }
+                sym_out[q] = s;
+            }
+        }
+    }
+
+    // ring hand-over to the next call: the volumes of the last complete block, or the unchanged ring without one
+    if (b == nfull - 1) {
+        ChannelState* so = p.state_out + ch;
+#pragma unroll
+        for (int q = 0; q < CH; q++) so->vol_prev[j_first + q] = volr[q];
+    } else if (nfull == 0) {
+        ChannelState* so = p.state_out + ch;
+#pragma unroll
+        for (int q = 0; q < CH; q++) so->vol_prev[j_first + q] = pv[q];
+    }
+}
+
 }  // namespace
 
 struct dh_demod {
@@ -496,6 +877,15 @@ struct dh_demod {
     size_t pitch = 0;      // elements per work row
     size_t max_n = 0;      // chunk capacity of the work rows
     bool smem_attr_set = false;   // the kernel variant and its dynamic smem size are fixed per bank
+    // split mode (dh_demod_set_split): second state set, per-call block records and per-symbol {volume, average}
+    int split = 0;
+    ChannelState* d_state_set[2] = {nullptr, nullptr};   // d_state_set[0] == the set allocated at create
+    int scur = 0;                                        // d_state == d_state_set[scur]
+    int2* d_rec = nullptr;
+    int4* d_hdr = nullptr;
+    float2* d_va = nullptr;
+    size_t rec_pitch = 0;
+    bool split_attr_set = false;
 };
 
 namespace {
@@ -524,6 +914,36 @@ int demod_reserve(dh_demod* h, size_t max_n) {
     h->d_work[1] = nw[1];
     h->pitch = pitch;
     h->max_n = n4;
+    return DH_OK;
+}
+
+// split mode: blocks one call of n samples can touch per channel, counting the trailing partial one (every complete
+// block consumes at least 100 * sps - 1 samples of the at most carry_cap + n visible ones)
+size_t split_blocks(const dh_demod* h, size_t n) {
+    return ((size_t) h->carry_cap + n) / ((size_t) kBlockSyms * h->sps - 1) + 1;
+}
+
+// second state set + per-call scratch of the split kernels, grown on demand (scratch only: nothing to preserve)
+int split_reserve(dh_demod* h, size_t n) {
+    const size_t ch = h->channels;
+    if (!h->d_state_set[1]) {
+        DH_CUDA(cudaMalloc(&h->d_state_set[1], ch * sizeof(ChannelState)));
+        DH_CUDA(cudaMemset(h->d_state_set[1], 0, ch * sizeof(ChannelState)));
+    }
+    if (!h->d_hdr) DH_CUDA(cudaMalloc(&h->d_hdr, ch * sizeof(int4)));
+    const size_t need = split_blocks(h, n) + 1;
+    if (need > h->rec_pitch) {
+        DH_CUDA(cudaDeviceSynchronize());
+        cudaFree(h->d_rec);
+        cudaFree(h->d_va);
+        h->d_rec = nullptr;
+        h->d_va = nullptr;
+        h->rec_pitch = 0;
+        DH_CUDA(cudaMalloc(&h->d_rec, ch * need * sizeof(int2)));
+        DH_CUDA(cudaMalloc(&h->d_va, ch * need * kBlockSyms * sizeof(float2)));
+        DH_CUDA(cudaMemset(h->d_va, 0, ch * need * kBlockSyms * sizeof(float2)));
+        h->rec_pitch = need;
+    }
     return DH_OK;
 }
 
@@ -565,9 +985,20 @@ int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_leve
         delete h;
         return (int) e;
     }
+    h->d_state_set[0] = h->d_state;
+    static const int split_default = getenv("DH_DEMOD_SPLIT") ? atoi(getenv("DH_DEMOD_SPLIT")) : kSplitDefault;
+    h->split = split_default != 0;
     *out = h;
     return DH_OK;
 }
+
+int dh_demod_set_split(dh_demod* h, int enable) {
+    DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_set_split: handle is NULL");
+    h->split = enable != 0;
+    return DH_OK;
+}
+
+int dh_demod_kernels_per_call(const dh_demod* h) { return h && h->split ? 3 : 1; }
 
 int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reserve: handle is NULL");
@@ -669,6 +1100,75 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
                                          (int) smem));                                                               \
         demod_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                          \
     } while (0)
+    // ---- split mode: search chain -> per-symbol window sums -> per-block slicing (three kernels, same stream) ----
+    const size_t nblk = split_blocks(h, n);                                      // blocks incl. the partial one
+    const size_t vol_tiles = (nblk * kBlockSyms + kVolThreads - 1) / kVolThreads;
+    if (h->split && nblk <= 65535 && vol_tiles <= 65535) {
+        int rc = split_reserve(h, n);
+        if (rc != DH_OK) return rc;
+        p.state = h->d_state_set[h->scur];
+        p.state_out = h->d_state_set[h->scur ^ 1];
+        p.rec = h->d_rec;
+        p.hdr = h->d_hdr;
+        p.va = h->d_va;
+        p.rec_pitch = (int) h->rec_pitch;
+        static const int prefetch = getenv("DH_DEMOD_PREFETCH") ? atoi(getenv("DH_DEMOD_PREFETCH")) : 1;
+        p.prefetch = prefetch;
+#define DH_LAUNCH_SEARCH(GG, SS, TT)                                                                                 \
+    do {                                                                                                             \
+        if (!h->split_attr_set)                                                                                      \
+            DH_CUDA(cudaFuncSetAttribute(demod_search_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                         (int) smem));                                                               \
+        demod_search_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                   \
+    } while (0)
+        if (G == 10 && h->sps == 10) {
+            DH_LAUNCH_SEARCH(10, 10, kThreads);
+        } else if (G == 10 && h->sps == 20) {
+            DH_LAUNCH_SEARCH(10, 20, kThreads);
+        } else if (G == 20 && h->sps == 20) {
+            DH_LAUNCH_SEARCH(20, 20, kThreads);
+        } else if (G == 20) {
+            DH_LAUNCH_SEARCH(20, 40, kThreads);
+        } else if (G == 10) {
+            DH_LAUNCH_SEARCH(10, 40, 32);
+        } else if (G == 16) {
+            DH_LAUNCH_SEARCH(16, 0, kThreads);
+        } else {
+            DH_LAUNCH_SEARCH(32, 0, kThreads);
+        }
+#undef DH_LAUNCH_SEARCH
+        DH_CUDA(cudaGetLastError());
+        const dim3 vgrid(h->channels, (unsigned) vol_tiles);
+        const size_t vsmem = (size_t) (kVolThreads / 32) * vol_warp_floats(h->sps) * sizeof(float);
+#define DH_LAUNCH_VOLUME(SS)                                                                                         \
+    do {                                                                                                             \
+        if (!h->split_attr_set)                                                                                      \
+            DH_CUDA(cudaFuncSetAttribute(demod_volume_kernel<SS>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                         (int) vsmem));                                                              \
+        demod_volume_kernel<SS><<<vgrid, kVolThreads, vsmem, st>>>(p);                                                \
+    } while (0)
+        if (fast && h->sps == 10) {
+            DH_LAUNCH_VOLUME(10);
+        } else if (fast && h->sps == 20) {
+            DH_LAUNCH_VOLUME(20);
+        } else if (fast) {
+            DH_LAUNCH_VOLUME(40);
+        } else {
+            DH_LAUNCH_VOLUME(0);
+        }
+#undef DH_LAUNCH_VOLUME
+        DH_CUDA(cudaGetLastError());
+        const unsigned sgroups = (kThreads / 32) * (32 / kSliceG);
+        const dim3 sgrid((h->channels + sgroups - 1) / sgroups, (unsigned) nblk);
+        demod_slice_kernel<<<sgrid, kThreads, 0, st>>>(p);
+        DH_CUDA(cudaGetLastError());
+        h->split_attr_set = true;
+        h->scur ^= 1;
+        h->d_state = h->d_state_set[h->scur];   // reset / export / import address the current set
+        h->cur ^= 1;
+        return DH_OK;
+    }
+
     static const int minb = getenv("DH_DEMOD_MINB") ? atoi(getenv("DH_DEMOD_MINB")) : 0;   // experiment switch
     if (G == 10 && h->sps == 10 && minb == 10) {
         DH_LAUNCH_DEMOD4(10, 10, kThreads, 10);
@@ -768,7 +1268,11 @@ int dh_demod_state_import(dh_demod* h, const void* h_buf, size_t bytes, void* st
 void dh_demod_destroy(dh_demod* h) {
     if (!h) return;
     dh::DeviceGuard guard(h->device);
-    cudaFree(h->d_state);
+    cudaFree(h->d_state_set[0]);
+    cudaFree(h->d_state_set[1]);
+    cudaFree(h->d_rec);
+    cudaFree(h->d_hdr);
+    cudaFree(h->d_va);
     cudaFree(h->d_work[0]);
     cudaFree(h->d_work[1]);
     delete h;

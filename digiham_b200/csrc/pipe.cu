@@ -170,7 +170,7 @@ int run_stages(dh_pipe* h, const void* d_in, size_t in_pitch, size_t n, cudaStre
                               k23);
     }
     if (rc != DH_OK) return rc;
-    h->launches++;
+    h->launches += (uint64_t) dh_demod_kernels_per_call(h->demod);
     if ((rc = mark(k23)) != DH_OK) return rc;
     if (k2_done) DH_CUDA(cudaEventRecord(k2_done, k23));
     if ((rc = mark(k23)) != DH_OK) return rc;
@@ -476,6 +476,7 @@ int dh_pipe_collect(dh_pipe* h, void* stream) {
 }
 
 dh_decoder* dh_pipe_decoder(dh_pipe* h) { return h ? h->decoder : nullptr; }
+dh_demod* dh_pipe_demod(dh_pipe* h) { return h ? h->demod : nullptr; }
 
 // ---- state of the whole pipe: the blobs of its stages back to back behind a pipe header ----------------------------
 int dh_pipe_state_size(const dh_pipe* h, size_t* bytes) {

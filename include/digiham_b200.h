@@ -136,6 +136,15 @@ DH_API int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, siz
 DH_API int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_in, size_t in_pitch, size_t n,
                                  uint8_t* h_sym, size_t sym_pitch, uint32_t* h_nsym);
 DH_API uint32_t dh_demod_channels(const dh_demod* h);
+/* Schedule of dh_demod_process (results are identical either way; may be changed between any two calls).
+ * 0: one kernel, a lane group walks the 100-symbol blocks of its channel in order.  1: three kernels - only the
+ * variance search, whose +-1 nudge is the one sequential dependency of GfskDemodulator::process
+ * (src/gfsk_demodulator/gfsk_demodulator.cpp:41-80), walks the blocks in order; the window sums (:28-35) and the
+ * volume ring / slicing (:88-122) run one lane per symbol / one lane group per block.  New banks start with the
+ * library default (environment DH_DEMOD_SPLIT overrides it). */
+DH_API int dh_demod_set_split(dh_demod* h, int enable);
+/* kernels one dh_demod_process call launches with the current schedule */
+DH_API int dh_demod_kernels_per_call(const dh_demod* h);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);
 
@@ -270,6 +279,8 @@ DH_API int dh_pipe_collect_step(dh_pipe* h);
 DH_API int dh_pipe_collect(dh_pipe* h, void* stream);
 /* the decoder bank of the pipe: use dh_decoder_output / _meta / _totals / _clear / _set_slot_filter on it */
 DH_API dh_decoder* dh_pipe_decoder(dh_pipe* h);
+/* the demodulator bank of the pipe (dh_demod_set_split / dh_demod_kernels_per_call on it) */
+DH_API dh_demod* dh_pipe_demod(dh_pipe* h);
 /* device views of the symbols the demodulator produced in the LAST process call (parity artefact) */
 DH_API int dh_pipe_last_symbols(dh_pipe* h, const uint8_t** d_sym, size_t* sym_pitch, const uint32_t** d_nsym);
 /* Software pipelining inside one process call: the chunk is cut into sub-chunks of `sub_chunk` samples (multiple
