@@ -468,13 +468,13 @@ def main():
     pipe.set_async(not args.no_async)
     arm["pipelining"] = ("none" if args.no_async or wl["dominant"] != 0 else
                          "K1(i+1) overlaps K2+K3(i) on two streams (dh_pipe_set_async)")
-    arm["demod_schedule"] = ("split: search chain -> per-symbol window sums -> per-block slicing (3 kernels)"
-                             if pipe.demod_kernels_per_call == 3 else "one kernel")
     for _ in range(args.warmup):
         pipe.process(x, n=L)
         pipe.discard()
     pipe.sync()
     torch.cuda.synchronize()
+    arm["demod_schedule"] = ("split: search chain -> per-symbol window sums -> per-block slicing (3 kernels)"
+                             if pipe.demod_kernels_per_call == 3 else "one kernel")
     launches0 = pipe.launch_count
     barrier()
     torch.cuda.synchronize()

@@ -292,8 +292,9 @@ class DemodBank:
         return lib().dh_demod_max_symbols(self._h, n)
 
     def set_split(self, enable):
-        """dh_demod_set_split: one kernel (False) or search chain + per-symbol + per-block kernels (True)."""
-        check(lib().dh_demod_set_split(self._h, int(bool(enable))))
+        """dh_demod_set_split: one kernel (False), search chain + per-symbol + per-block kernels (True), or chosen
+        per call from the bank and call size (None, the default)."""
+        check(lib().dh_demod_set_split(self._h, -1 if enable is None else int(bool(enable))))
 
     @property
     def kernels_per_call(self):
@@ -455,7 +456,8 @@ class Pipe:
 
     def set_demod_split(self, enable):
         """Schedule of the pipe's demodulator bank (dh_demod_set_split on dh_pipe_demod)."""
-        check(lib().dh_demod_set_split(ctypes.c_void_p(lib().dh_pipe_demod(self._h)), int(bool(enable))))
+        check(lib().dh_demod_set_split(ctypes.c_void_p(lib().dh_pipe_demod(self._h)),
+                                       -1 if enable is None else int(bool(enable))))
 
     @property
     def demod_kernels_per_call(self):

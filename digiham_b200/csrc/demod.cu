@@ -38,8 +38,13 @@ constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (i
 // slower on B200 (0.42 vs 0.34 ms at 4096 channels: 342 CTAs are 1.15 waves of 2 x 148).
 constexpr int kThreads = 64;
 constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
-// dh_demod_set_split default of new banks (environment DH_DEMOD_SPLIT overrides it): see DESIGN.md, K2 split
-constexpr int kSplitDefault = 0;
+// dh_demod_set_split default of new banks (environment DH_DEMOD_SPLIT overrides it): -1 = by bank and call size.
+// Measured on B200 (profiles/r03_split_small_banks.txt, DMR pipe, 48000 samples per call): the split schedule is
+// 25 % faster per step at 1..32 channels, 16 % at 256, equal at 1024 and 11 % slower at 4096, where the one-kernel
+// form has enough channels in flight and the split pays for reading the samples twice.
+constexpr int kSplitDefault = -1;
+constexpr uint32_t kSplitAutoChannels = 512;   // auto: banks up to this size ...
+constexpr size_t kSplitAutoBlocks = 8;         // ... and calls that span at least this many 100-symbol blocks
 
 struct ChannelState {
     float vol_prev[kBlockSyms];  // volume ring content written by the previous block (zeros at power-on)
@@ -878,7 +883,8 @@ struct dh_demod {
     size_t max_n = 0;      // chunk capacity of the work rows
     bool smem_attr_set = false;   // the kernel variant and its dynamic smem size are fixed per bank
     // split mode (dh_demod_set_split): second state set, per-call block records and per-symbol {volume, average}
-    int split = 0;
+    int split = 0;                 // -1 auto, 0 one kernel, 1 three kernels
+    bool last_split = false;       // schedule of the most recent process call
     ChannelState* d_state_set[2] = {nullptr, nullptr};   // d_state_set[0] == the set allocated at create
     int scur = 0;                                        // d_state == d_state_set[scur]
     int2* d_rec = nullptr;
@@ -987,18 +993,22 @@ int dh_demod_create(dh_demod** out, int device, uint32_t channels, int four_leve
     }
     h->d_state_set[0] = h->d_state;
     static const int split_default = getenv("DH_DEMOD_SPLIT") ? atoi(getenv("DH_DEMOD_SPLIT")) : kSplitDefault;
-    h->split = split_default != 0;
+    h->split = split_default < 0 ? -1 : (split_default != 0);
     *out = h;
     return DH_OK;
 }
 
 int dh_demod_set_split(dh_demod* h, int enable) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_set_split: handle is NULL");
-    h->split = enable != 0;
+    h->split = enable < 0 ? -1 : (enable != 0);
     return DH_OK;
 }
 
-int dh_demod_kernels_per_call(const dh_demod* h) { return h && h->split ? 3 : 1; }
+int dh_demod_kernels_per_call(const dh_demod* h) {
+    if (!h) return 0;
+    if (h->split >= 0) return h->split ? 3 : 1;
+    return h->last_split ? 3 : 1;
+}
 
 int dh_demod_reserve(dh_demod* h, size_t max_n, float** d_buf, size_t* pitch) {
     DH_REQUIRE(h != nullptr, DH_E_INVALID, "dh_demod_reserve: handle is NULL");
@@ -1103,7 +1113,10 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
     // ---- split mode: search chain -> per-symbol window sums -> per-block slicing (three kernels, same stream) ----
     const size_t nblk = split_blocks(h, n);                                      // blocks incl. the partial one
     const size_t vol_tiles = (nblk * kBlockSyms + kVolThreads - 1) / kVolThreads;
-    if (h->split && nblk <= 65535 && vol_tiles <= 65535) {
+    const bool want_split = h->split > 0 || (h->split < 0 && h->channels <= kSplitAutoChannels && nblk >= kSplitAutoBlocks);
+    h->last_split = false;
+    if (want_split && nblk <= 65535 && vol_tiles <= 65535) {
+        h->last_split = true;
         int rc = split_reserve(h, n);
         if (rc != DH_OK) return rc;
         p.state = h->d_state_set[h->scur];

@@ -137,13 +137,14 @@ DH_API int dh_demod_process_host(dh_demod* h, uint32_t channels, const float* h_
                                  uint8_t* h_sym, size_t sym_pitch, uint32_t* h_nsym);
 DH_API uint32_t dh_demod_channels(const dh_demod* h);
 /* Schedule of dh_demod_process (results are identical either way; may be changed between any two calls).
- * 0: one kernel, a lane group walks the 100-symbol blocks of its channel in order.  1: three kernels - only the
- * variance search, whose +-1 nudge is the one sequential dependency of GfskDemodulator::process
- * (src/gfsk_demodulator/gfsk_demodulator.cpp:41-80), walks the blocks in order; the window sums (:28-35) and the
- * volume ring / slicing (:88-122) run one lane per symbol / one lane group per block.  New banks start with the
- * library default (environment DH_DEMOD_SPLIT overrides it). */
-DH_API int dh_demod_set_split(dh_demod* h, int enable);
-/* kernels one dh_demod_process call launches with the current schedule */
+ * 0: one kernel, a lane group walks the 100-symbol blocks of its channel in order (best for thousands of channels).
+ * 1: three kernels - only the variance search, whose +-1 nudge is the one sequential dependency of
+ * GfskDemodulator::process (src/gfsk_demodulator/gfsk_demodulator.cpp:41-80), walks the blocks in order; the
+ * window sums (:28-35) and the volume ring / slicing (:88-122) run one lane per symbol / one lane group per block
+ * (lower latency for small banks).  -1 (the default of new banks; environment DH_DEMOD_SPLIT overrides it):
+ * chosen per call from the bank size and the number of blocks the call spans. */
+DH_API int dh_demod_set_split(dh_demod* h, int mode);
+/* kernels a dh_demod_process call launches: with a fixed schedule, else those of the most recent call */
 DH_API int dh_demod_kernels_per_call(const dh_demod* h);
 DH_API int dh_demod_reset(dh_demod* h, void* stream);
 DH_API void dh_demod_destroy(dh_demod* h);

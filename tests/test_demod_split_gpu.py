@@ -121,10 +121,7 @@ def _run(proto, x, n, chunk, split, async_mode):
         blk = torch.zeros((C, (c + 3) & ~3), dtype=torch.float32, device="cuda")
         blk[:, :c] = x[:, pos:pos + c]
         pipe.process(blk, n=c)
-        if async_mode:
-            pipe.sync()
-            torch.cuda.synchronize()
-    pipe.collect()
+        pipe.collect()           # syncs an asynchronous pipe first; the device result slots hold two calls at most
     res = [(pipe.output(ch), pipe.meta(ch)) for ch in range(C)]
     pipe.close()
     return res
@@ -183,3 +180,34 @@ def test_split_other_pipes_equal_reference(proto_name):
     assert sum(len(r[0]) + len(r[1]) for r in got) > 0
     for ch in range(C):
         assert got[ch][0] == outs[ch].tobytes() and got[ch][1] == metas[ch], ch
+
+
+def test_split_auto_policy_follows_bank_and_call_size():
+    """Default (-1): small banks use the three-kernel schedule for calls that span many blocks, the one-kernel
+    schedule for short calls and for large banks; the symbol stream does not notice the changes."""
+    import digiham_b200 as dh
+    orc = oracle_lib.best()
+    C, sps = 5, 10
+    x = _signals(C, 2600, sps, seed=17)
+    n = x.shape[1]
+    bank = dh.DemodBank(C, sps=sps)
+    bank.set_split(None)
+    outs = [[] for _ in range(C)]
+    pos = 0
+    seen = set()
+    for c in [12000, 700, 3000, 9000, n - 24700]:
+        d = torch.from_numpy(np.ascontiguousarray(x[:, pos:pos + c])).cuda()
+        sym, nsym = bank.process(d)
+        seen.add((c >= 8000, bank.kernels_per_call))
+        sym, nsym = sym.cpu().numpy(), nsym.cpu().numpy()
+        for ch in range(C):
+            outs[ch].append(sym[ch, :nsym[ch]].copy())
+        pos += c
+    assert seen == {(True, 3), (False, 1)}, seen
+    for ch in range(C):
+        assert np.array_equal(np.concatenate(outs[ch]), orc.demod(x[ch], sps=sps)), ch
+    bank.close()
+    big = dh.DemodBank(1024, sps=sps)
+    big.process(torch.zeros((1024, 12000), dtype=torch.float32, device="cuda"))
+    assert big.kernels_per_call == 1
+    big.close()
