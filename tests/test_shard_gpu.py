@@ -72,7 +72,8 @@ def test_shard_world1_pack_and_sink(s16):
         assert sp.output(c) == outs[c].tobytes(), c
         assert sp.meta(c) == metas[c], c
     launches, _, d2h = sp.stats()
-    assert launches == steps * 4 and d2h > 0      # K1, K2, decoder, pack per step
+    # K1, K2, decoder, pack per step; K2 is three kernels when the bank is small enough for the split schedule
+    assert launches in (steps * 4, steps * 6) and d2h > 0
     sp.close()
 
 
