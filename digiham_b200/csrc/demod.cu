@@ -80,7 +80,6 @@ struct DemodParams {
                                  //             carry_len at entry}
     float2* va;                  // [channels][rec_pitch * 100] {volume, average} of every symbol of this call
     int rec_pitch;
-    int prefetch;                // search kernel: pull the next block's lines into L2 while the current one is searched
 };
 
 __device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
@@ -98,9 +97,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dh::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void prefetch_l2(const void* gmem) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -604,15 +600,6 @@ __global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_cons
     }
     while (m == kBlockSyms) {
         const int a0 = view.align_of(P);
-        // where the next block starts does not depend on the search result: pull its 128-byte lines towards L2 now,
-        // so that the staging copies issued right after the search do not wait for DRAM
-        if (p.prefetch) {
-            const int Pn = P + kBlockSyms * sps + vo;
-            const int end = min(Pn + full_len, T);
-            if (end > Pn && (view.ext_row == nullptr || Pn >= carry_len)) {
-                for (int x = Pn + gl * 32; x < end + 31; x += G * 32) prefetch_l2(view.at(min(x, end - 1)));
-            }
-        }
         // variance-minimum phase search over the 100 windows of the block (gfsk_demodulator.cpp:41-80)
         for (int i = gl; i < sps; i += G) {
             const float* w0 = S + a0 + i;
@@ -1125,8 +1112,6 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         p.hdr = h->d_hdr;
         p.va = h->d_va;
         p.rec_pitch = (int) h->rec_pitch;
-        static const int prefetch = getenv("DH_DEMOD_PREFETCH") ? atoi(getenv("DH_DEMOD_PREFETCH")) : 1;
-        p.prefetch = prefetch;
 #define DH_LAUNCH_SEARCH(GG, SS, TT)                                                                                 \
     do {                                                                                                             \
         if (!h->split_attr_set)                                                                                      \

@@ -1,7 +1,7 @@
 """Step latency of the DMR pipe against the bank size for the two K2 schedules (dh_demod_set_split).
 The one-kernel demodulator walks the 100-symbol blocks of a channel in order, so its duration does not shrink with
 the bank; the split schedule only keeps the variance search on that chain.
-usage: split_small_banks.py [steps]"""
+usage: split_small_banks.py [steps] [channels,channels,...]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -10,7 +10,8 @@ from digiham_b200 import synth
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 20
 L = 48000
-for C in (1, 32, 256, 1024, 2048, 4096):
+banks = [int(v) for v in sys.argv[2].split(',')] if len(sys.argv) > 2 else [1, 32, 256, 1024, 2048, 4096]
+for C in banks:
     x, _ = synth.dmr_channel_bank(C, L, seed=1, device="cuda:0")
     row = []
     for split in (False, True):
