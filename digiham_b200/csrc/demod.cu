@@ -80,6 +80,7 @@ struct DemodParams {
                                  //             carry_len at entry}
     float2* va;                  // [channels][rec_pitch * 100] {volume, average} of every symbol of this call
     int rec_pitch;
+    int search_dbuf;             // search kernel: two sample buffers per group (next block staged during the search)
 };
 
 __device__ __forceinline__ float min_lt(float cur, float v) { return v < cur ? v : cur; }
@@ -577,8 +578,11 @@ __global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_cons
     const unsigned gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << (grp_in_warp * G);
 
     const int sps = SPS > 0 ? SPS : p.sps;
-    float* S = smem + (size_t) grp * p.group_floats;
-    double* var = reinterpret_cast<double*>(S + p.samples_cap);
+    // one or two sample buffers (p.search_dbuf), then the phase variances
+    float* const Sbuf0 = smem + (size_t) grp * p.group_floats;
+    float* const Sbuf1 = p.search_dbuf ? Sbuf0 + p.samples_cap : Sbuf0;
+    double* var = reinterpret_cast<double*>(Sbuf0 + (p.search_dbuf ? 2 : 1) * p.samples_cap);
+    float* S = Sbuf0;        // buffer that holds the current block
 
     const ChannelState* st = p.state + ch;
     int vo = st->vo;
@@ -600,13 +604,24 @@ __global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_cons
     }
     while (m == kBlockSyms) {
         const int a0 = view.align_of(P);
-        // variance-minimum phase search over the 100 windows of the block (gfsk_demodulator.cpp:41-80)
+        // Where the next block starts does not depend on the outcome of this search, only whether it is complete
+        // does: with two buffers its samples are requested now and arrive while this block is searched.  It can only
+        // be complete if at least 100 * sps + 1 samples are visible from its start.
+        const int P_next = P + kBlockSyms * sps + vo;
+        float* const S_other = S == Sbuf0 ? Sbuf1 : Sbuf0;
+        const bool prestaged = p.search_dbuf && T - P_next >= kBlockSyms * sps + 1;
+        if (prestaged) view.stage<G>(S_other, P_next, full_len, gl);
+        // variance-minimum phase search over the 100 windows of the block (gfsk_demodulator.cpp:41-80).  This kernel
+        // is nothing but these two ordered chains, so on the compile-time paths they are fully unrolled: the 100
+        // samples of a phase stay in registers between the two passes and their loads / conversions are scheduled
+        // ahead of the dependent FADD / DADD chain (134 registers; demod_kernel keeps `#pragma unroll 11` because its
+        // slicer state already fills the register file)
         for (int i = gl; i < sps; i += G) {
             const float* w0 = S + a0 + i;
             const float* wv = w0 + vo;          // windows 1..99 are shifted by the pending nudge
             float total = __fadd_rn(0.0f, w0[0]);
             if (SPS > 0) {
-#pragma unroll 11
+#pragma unroll
                 for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * SPS]);
             } else {
                 for (int k = 1; k < kBlockSyms; k++) total = __fadd_rn(total, wv[k * sps]);
@@ -615,7 +630,7 @@ __global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_cons
             double d = __dsub_rn(mean, (double) w0[0]);
             double dsum = __dadd_rn(0.0, __dmul_rn(d, d));
             if (SPS > 0) {
-#pragma unroll 11
+#pragma unroll
                 for (int k = 1; k < kBlockSyms; k++) {
                     d = __dsub_rn(mean, (double) wv[k * SPS]);
                     dsum = __dadd_rn(dsum, __dmul_rn(d, d));
@@ -646,10 +661,10 @@ __global__ void __launch_bounds__(THREADS) demod_search_kernel(const __grid_cons
         } else if (vpos >= sps / 2 && vpos < sps - 1) {
             vo_next = -1;
         }
-        const int P_next = P + kBlockSyms * sps + vo;
         const int m_next = processable(T, P_next, vo_next, sps);
         __syncwarp(gmask);   // every lane of the group is done with the staged block and with var[]
-        if (m_next == kBlockSyms) view.stage<G>(S, P_next, full_len, gl);
+        if (m_next == kBlockSyms && !prestaged) view.stage<G>(S_other, P_next, full_len, gl);
+        S = S_other;
         nfull++;
         P = P_next;
         vo = vo_next;
@@ -1112,12 +1127,21 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         p.hdr = h->d_hdr;
         p.va = h->d_va;
         p.rec_pitch = (int) h->rec_pitch;
+        // two sample buffers per group when they fit comfortably (always on the compile-time paths)
+        const int group_floats_mono = p.group_floats;
+        int group_floats_dbuf = p.group_floats + p.samples_cap;
+        // keep the group segments 12 banks apart (see above) with the second buffer in between
+        if (h->sps == 10 || h->sps == 20) group_floats_dbuf += (12 - group_floats_dbuf % 32 + 32) % 32;
+        const size_t smem_dbuf = (size_t) groups * group_floats_dbuf * sizeof(float);
+        p.search_dbuf = smem_dbuf <= 160 * 1024;
+        const size_t smem_search = p.search_dbuf ? smem_dbuf : smem;
+        if (p.search_dbuf) p.group_floats = group_floats_dbuf;
 #define DH_LAUNCH_SEARCH(GG, SS, TT)                                                                                 \
     do {                                                                                                             \
         if (!h->split_attr_set)                                                                                      \
             DH_CUDA(cudaFuncSetAttribute(demod_search_kernel<GG, SS, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                         (int) smem));                                                               \
-        demod_search_kernel<GG, SS, TT><<<grid, TT, smem, st>>>(p);                                                   \
+                                         (int) smem_search));                                                        \
+        demod_search_kernel<GG, SS, TT><<<grid, TT, smem_search, st>>>(p);                                            \
     } while (0)
         if (G == 10 && h->sps == 10) {
             DH_LAUNCH_SEARCH(10, 10, kThreads);
@@ -1136,6 +1160,7 @@ int dh_demod_process(dh_demod* h, const float* d_in, size_t in_pitch, size_t n, 
         }
 #undef DH_LAUNCH_SEARCH
         DH_CUDA(cudaGetLastError());
+        p.group_floats = group_floats_mono;
         const dim3 vgrid(h->channels, (unsigned) vol_tiles);
         const size_t vsmem = (size_t) (kVolThreads / 32) * vol_warp_floats(h->sps) * sizeof(float);
 #define DH_LAUNCH_VOLUME(SS)                                                                                         \
