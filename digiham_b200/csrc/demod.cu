@@ -39,11 +39,12 @@ constexpr int kBlockSyms = 100;  // VARIANCE_SYMBOLS == VOLUME_RB_SIZE == 100 (i
 constexpr int kThreads = 64;
 constexpr int kCarrySlack = 16;  // carry_cap = 100 * sps + kCarrySlack
 // dh_demod_set_split default of new banks (environment DH_DEMOD_SPLIT overrides it): -1 = by bank and call size.
-// Measured on B200 (profiles/r03_split_small_banks.txt, DMR pipe, 48000 samples per call): the split schedule is
-// 25 % faster per step at 1..32 channels, 16 % at 256, equal at 1024 and 11 % slower at 4096, where the one-kernel
-// form has enough channels in flight and the split pays for reading the samples twice.
+// Measured on B200 (profiles/r02_split_small_banks.txt, DMR pipe, 48000 samples per call): the split schedule is
+// 42 % faster per step at 1 channel, 39 % at 32, 30 % at 256, 22 % at 512, 10 % at 1024, equal at 2048 and 11 %
+// slower at 4096, where the one-kernel form has enough channels in flight and the split pays for reading the
+// samples twice.
 constexpr int kSplitDefault = -1;
-constexpr uint32_t kSplitAutoChannels = 512;   // auto: banks up to this size ...
+constexpr uint32_t kSplitAutoChannels = 1024;  // auto: banks up to this size ...
 constexpr size_t kSplitAutoBlocks = 8;         // ... and calls that span at least this many 100-symbol blocks
 
 struct ChannelState {

@@ -207,7 +207,7 @@ def test_split_auto_policy_follows_bank_and_call_size():
     for ch in range(C):
         assert np.array_equal(np.concatenate(outs[ch]), orc.demod(x[ch], sps=sps)), ch
     bank.close()
-    big = dh.DemodBank(1024, sps=sps)
-    big.process(torch.zeros((1024, 12000), dtype=torch.float32, device="cuda"))
+    big = dh.DemodBank(2048, sps=sps)
+    big.process(torch.zeros((2048, 12000), dtype=torch.float32, device="cuda"))
     assert big.kernels_per_call == 1
     big.close()
