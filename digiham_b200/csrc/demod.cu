@@ -22,6 +22,10 @@
 // from the caller's rows (DemodParams::ext).  Partially filled blocks are carried: the unconsumed tail of every
 // channel is moved right-aligned in front of the position where the next chunk starts, in the other of two
 // alternating work-row sets.
+//
+// Small banks (up to 1024 channels by default, dh_demod_set_split) run the same arithmetic as three kernels instead:
+// only the variance search walks the blocks in order, window sums and slicing run one lane per symbol / one lane
+// group per block (see "Split form of K2" below); with few channels the block chain is the whole step.
 #include "common.cuh"
 
 #include <cstring>
